@@ -1,0 +1,197 @@
+"""Generate the golden fixtures under tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, read-only) in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference needs `diffusers` base classes only; tests/golden/_standin provides
+them.  All noise is routed through a seeded CPU generator (tests/toy_models.seeded_noise) and the toy
+score models are bit-reproducible across devices, so the fixtures replay exactly on the GPU box, where
+/root/reference does not exist.  Fixtures are small (< 1.5 MB total) and committed.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(HERE, "_standin"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+from tests.helpers import l4_sampling_loop  # noqa: E402
+from tests.toy_models import ToyADM, ToySDUNet, seeded_noise  # noqa: E402
+
+SU = "diffusion_uncertainty.schedulers_uncertainty."
+
+
+def quiet():
+    return contextlib.redirect_stdout(io.StringIO())
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if torch.is_tensor(v):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path) / 1024:.1f} KiB)")
+
+
+def base_config(**over):
+    cfg = dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear",
+               clip_sample=True, set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon",
+               timestep_spacing="leading")
+    cfg.update(over)
+    return cfg
+
+
+def run_scheduler_case(name, module, cls_name, ctor_kw, n_steps, B=4, C=3, H=16, seed=0, eta=0.0,
+                       dropout=False, cfg_over=None, model_scale=1.0):
+    import importlib
+    mod = importlib.import_module(SU + module)
+    cls = getattr(mod, cls_name)
+    model = ToyADM(C, seed=seed, dropout=dropout, scale=model_scale).eval()
+    g = torch.Generator().manual_seed(100 + seed)
+    x_T = torch.randn(B, C, H, H, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    with quiet():
+        sched = cls.from_config(base_config(**(cfg_over or {})), unet=model, **ctor_kw)
+        sched.set_timesteps(n_steps)
+        with seeded_noise(1000 + seed):
+            res = l4_sampling_loop(sched, model, x_T, y, eta=eta)
+    keep = [0, len(res["prevs"]) // 2, len(res["prevs"]) - 1]
+    save(name, x_T=x_T, y=y, final=res["final"], uncertainty=res["uncertainty"], score=res["score"],
+         prev_first=res["prevs"][keep[0]], prev_mid=res["prevs"][keep[1]],
+         timesteps=sched.timesteps, after=sched.timestep_after_step, end=sched.timestep_end_step)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+
+    # ---- A: the BASELINE scheduler (uncertainty_zigzag_centered), through the reference's own L4 loop too
+    run_scheduler_case("sched_zigzag_centered", "scheduling_ddim_uncertainty_zigzag_centered",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=40, num_steps_uc=10, num_zigzag=3), n_steps=50)
+    run_scheduler_case("sched_zigzag_centered_eta", "scheduling_ddim_uncertainty_zigzag_centered",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=3, after_step=5, num_steps_uc=4, num_zigzag=2), n_steps=20, seed=1, eta=0.3,
+                       cfg_over=dict(beta_schedule="squaredcos_cap_v2", clip_sample=False))
+    import diffusion_uncertainty.generate_samples as gs
+    mod = __import__(SU + "scheduling_ddim_uncertainty_zigzag_centered", fromlist=["x"])
+    model = ToyADM(3, seed=0).eval()
+    g = torch.Generator().manual_seed(100)
+    x_T = torch.randn(6, 3, 16, 16, generator=g)
+    y = torch.randint(0, 10, (6,), generator=g)
+    with quiet():
+        sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
+            base_config(), unet=model, M=5, after_step=40, num_steps_uc=10, num_zigzag=3)
+        sched.set_timesteps(50)
+        with seeded_noise(77):
+            res = gs.generate_samples_model_scheduler_class_conditioned_from_tensor(
+                X_T=x_T, y=y, batch_size=4, device=torch.device("cpu"), model=model, scheduler=sched)
+    save("l4_zigzag_centered", x_T=x_T, y=y, gen_images=res["gen_images"], uncertainty=res["uncertainty"],
+         score=res["score"])
+
+    # ---- other scheduler variants
+    run_scheduler_case("sched_zigzag", "scheduling_ddim_uncertainty_zigzag",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=4, after_step=10, num_steps_uc=5, num_zigzag=2), n_steps=20, seed=2)
+    run_scheduler_case("sched_centered", "scheduling_ddim_uncertainty_centered",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=10, num_steps_uc=5, predict_next=False), n_steps=20, seed=3)
+    run_scheduler_case("sched_centered_next", "scheduling_ddim_uncertainty_centered",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=10, num_steps_uc=5, predict_next=True), n_steps=20, seed=4)
+    run_scheduler_case("sched_infer_noise", "scheduling_ddim_infer_noise",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=10, num_steps_uc=5, predict_next=False), n_steps=20, seed=5)
+    run_scheduler_case("sched_mc_dropout", "scheduling_ddim_mc_dropout",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=6, after_step=10, num_steps_uc=5), n_steps=20, seed=6, dropout=True)
+    run_scheduler_case("sched_threshold_max", "scheduling_ddim_uncertainty_threshold",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=10, num_steps_uc=5, uncertainty_threshold=1.0,
+                            uncertainty_threshold_mode="max"), n_steps=20, seed=7)
+    run_scheduler_case("sched_threshold_min", "scheduling_ddim_uncertainty_threshold",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=10, num_steps_uc=5, uncertainty_threshold=0.5,
+                            uncertainty_threshold_mode="min", predict_next=True), n_steps=20, seed=8)
+    run_scheduler_case("sched_multiscale", "scheduling_ddim_infer_noise_multiscale_threshold",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=5, after_step=10, num_steps_uc=5), n_steps=20, seed=9)
+
+    # ---- F2a / F2b: calculate_threshold_map
+    from diffusion_uncertainty.pipeline_uncertainty import \
+        pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution as pd
+    g = torch.Generator().manual_seed(5)
+    arrays = {}
+    cases = [("a", (4, 3, 16, 16), 0.9, "higher"), ("b", (4, 3, 16, 16), 0.95, "lower"),
+             ("c", (2, 4, 32, 32), 0.9, "higher"), ("d", (3, 100, 7), 0.5, "higher"),
+             ("e", (5, 7), 0.99, "higher"), ("f", (2, 3, 64, 64), 0.9, "higher")]
+    for tag, shape, q, kind in cases:
+        u = torch.rand(shape, generator=g) ** 3
+        if tag == "c":  # heavy ties: quantise
+            u = (u * 16).round() / 16
+        if tag == "f":  # a NaN row
+            u[1, 0, 0, 0] = float("nan")
+        arrays[f"{tag}_u"] = u
+        arrays[f"{tag}_q"] = q
+        arrays[f"{tag}_higher"] = kind == "higher"
+        arrays[f"{tag}_mask"] = pd.calculate_threshold_map(float(q), None, u, kind)
+        arrays[f"{tag}_thr"] = torch.quantile(u.flatten(1).float(), q, dim=1)
+    thr_map = torch.rand(6, 3, 16, 16, generator=g) ** 3
+    u = torch.rand(4, 3, 16, 16, generator=g) ** 3
+    arrays["t_u"], arrays["t_thr"] = u, thr_map
+    arrays["t_mask_hi"] = pd.calculate_threshold_map(thr_map, 2, u, "higher")
+    arrays["t_mask_lo"] = pd.calculate_threshold_map(thr_map, 3, u, "lower")
+    save("threshold_map", **arrays)
+
+    # ---- F1c + F2a + F5: estimate_score_update_posterior (batch-sum quirk at B=4)
+    model = ToyADM(3, seed=11).eval()
+    g = torch.Generator().manual_seed(11)
+    B = 4
+    x = torch.randn(B, 3, 16, 16, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    t_tensor = torch.full((B,), 300, dtype=torch.long)
+    alphas_cumprod = torch.cumprod(1 - torch.linspace(1e-4, 0.02, 1000), 0)
+    a_hat = alphas_cumprod[30]
+    with torch.no_grad(), seeded_noise(11):
+        eps = model(x, t_tensor, y=y)[:, :3]
+        u, post = pd.estimate_score_update_posterior(5, model, None, x, y, t_tensor, eps, x.clone(), a_hat)
+    mask = pd.calculate_threshold_map(0.9, None, u, "higher")
+    eps_new = post * mask + eps * (1 - mask)
+    save("posterior_update", x=x, y=y, eps=eps, u=u, post=post, mask=mask, eps_new=eps_new, a_hat=a_hat, t=300, M=5)
+
+    # ---- SD percentile guidance fn (posterior and gradient modes), B=1 with CFG-doubled input
+    import diffusion_uncertainty.uncertainty_guidance as ug
+    sd = ToySDUNet(4, seed=12).eval()
+    g = torch.Generator().manual_seed(12)
+    lat = torch.randn(1, 4, 32, 32, generator=g)
+    lat2 = torch.cat([lat] * 2)
+    emb = torch.randn(2, 8, 16, generator=g)
+    t_tensor = torch.tensor(501)
+    a_hat = alphas_cumprod[501]
+    out = {}
+    for mode, use_post in (("post", True), ("grad", False)):
+        ug.use_posterior = use_post
+        with seeded_noise(12), quiet():
+            un, tx = sd(lat2, t_tensor, emb)[0].chunk(2)
+            eps = (un + 7.5 * (tx - un)).detach().clone()
+            res = ug.get_uncertainty_guided_score_with_percentile(
+                eps, lat2.clone(), t_tensor, emb.clone(), sd, a_hat, 0.9, "stable-diffusion",
+                num_uncertainty_samples=5, guidance_scale=7.5, lr=0.7)
+        out[f"{mode}_eps"] = eps.detach()
+        out[f"{mode}_out"] = res.detach()
+    ug.use_posterior = True
+    save("sd_percentile_guidance", lat=lat, emb=emb, t=501, a_hat=a_hat, **out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,31 @@
+"""Shared test drivers (used by tests/ and by tests/golden/make_golden.py)."""
+import torch
+
+
+def l4_sampling_loop(scheduler, model, x_T, y, eta=0.0, slice_channels=None):
+    """The reference's L4 timestep loop around scheduler.step(), restated:
+    diffusion_uncertainty/generate_samples.py:175-201 (class-conditioned, from tensor).
+    Returns dict(final, uncertainty [B,T_uc,...] or None, score [B,T_uc,...] or None, prevs list)."""
+    x = x_T
+    C = slice_channels if slice_channels is not None else x_T.shape[1]
+    scheduler.prompt_embeds = y
+    uncs, scores, prevs = [], [], []
+    with torch.no_grad():
+        for t in scheduler.timesteps:
+            t = int(t.item())
+            t_tensor = torch.full((x.shape[0],), t, device=x.device, dtype=torch.long)
+            x = scheduler.scale_model_input(x, t)
+            eps = model(x, t_tensor, y=y)[:, :C]
+            out = scheduler.step(eps, t, x, eta=eta)
+            if scheduler.timestep_after_step >= t >= scheduler.timestep_end_step:
+                uncs.append(out.uncertainty.detach().cpu())
+                pe = out.pred_epsilon
+                scores.append(pe.detach().cpu())
+            x = out.prev_sample
+            prevs.append(x.detach().cpu())
+    return {
+        "final": x.detach().cpu(),
+        "uncertainty": torch.stack(uncs, dim=1) if uncs else None,
+        "score": torch.stack(scores, dim=1) if scores else None,
+        "prevs": prevs,
+    }

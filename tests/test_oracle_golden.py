@@ -1,0 +1,153 @@
+"""Pin the CPU oracle (oracle/du_oracle.py) against the golden vectors recorded from the UNMODIFIED
+reference (tests/golden/make_golden.py) and against known-answer facts of torch.quantile / torch.var
+(SURVEY.md §8c).  CPU-only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import du_oracle as O
+from tests.helpers import l4_sampling_loop
+from tests.toy_models import ToyADM, seeded_noise
+
+
+def load(golden_dir, name):
+    return {k: v for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def same(a, b):
+    """bit-for-bit, NaNs in the same places"""
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+SCHED_CASES = [
+    # name, variant, ctor kwargs, n_steps, seed, eta, dropout, cfg
+    ("sched_zigzag_centered", "zigzag_centered", dict(M=5, after_step=40, num_steps_uc=10, num_zigzag=3), 50, 0, 0.0, False, {}),
+    ("sched_zigzag_centered_eta", "zigzag_centered", dict(M=3, after_step=5, num_steps_uc=4, num_zigzag=2), 20, 1, 0.3, False,
+     dict(beta_schedule="squaredcos_cap_v2", clip_sample=False)),
+    ("sched_zigzag", "zigzag", dict(M=4, after_step=10, num_steps_uc=5, num_zigzag=2), 20, 2, 0.0, False, {}),
+    ("sched_centered", "centered", dict(M=5, after_step=10, num_steps_uc=5, predict_next=False), 20, 3, 0.0, False, {}),
+    ("sched_centered_next", "centered", dict(M=5, after_step=10, num_steps_uc=5, predict_next=True), 20, 4, 0.0, False, {}),
+    ("sched_infer_noise", "infer_noise", dict(M=5, after_step=10, num_steps_uc=5, predict_next=False), 20, 5, 0.0, False, {}),
+    ("sched_mc_dropout", "mc_dropout", dict(M=6, after_step=10, num_steps_uc=5), 20, 6, 0.0, True, {}),
+    ("sched_threshold_max", "threshold", dict(M=5, after_step=10, num_steps_uc=5, uncertainty_threshold=1.0,
+                                              uncertainty_threshold_mode="max"), 20, 7, 0.0, False, {}),
+    ("sched_threshold_min", "threshold", dict(M=5, after_step=10, num_steps_uc=5, uncertainty_threshold=0.5,
+                                              uncertainty_threshold_mode="min", predict_next=True), 20, 8, 0.0, False, {}),
+    ("sched_multiscale", "multiscale", dict(M=5, after_step=10, num_steps_uc=5), 20, 9, 0.0, False, {}),
+]
+
+
+@pytest.mark.parametrize("case", SCHED_CASES, ids=[c[0] for c in SCHED_CASES])
+def test_oracle_scheduler_matches_reference(golden_dir, case):
+    name, variant, kw, n_steps, seed, eta, dropout, cfg = case
+    g = load(golden_dir, name)
+    model = ToyADM(3, seed=seed, dropout=dropout).eval()
+    x_T, y = T(g["x_T"]), T(g["y"])
+    sched = O.OracleScheduler(variant, None, unet=model, **kw, **cfg)
+    sched.predict = lambda x, t: model(x, t, y=sched.prompt_embeds)[:, :3]
+    sched.set_timesteps(n_steps)
+    assert sched.timestep_after_step == int(g["after"]) and sched.timestep_end_step == int(g["end"])
+    assert same(sched.timesteps.numpy(), g["timesteps"])
+    with seeded_noise(1000 + seed):
+        res = l4_sampling_loop(sched, model, x_T, y, eta=eta)
+    # the oracle repeats the reference's fp32 operations one for one -> bit-exact on CPU
+    assert same(res["uncertainty"].numpy(), g["uncertainty"])
+    assert same(res["score"].numpy(), g["score"])
+    assert same(res["final"].numpy(), g["final"])
+
+
+def test_quantile_restatement_is_torch_quantile(golden_dir):
+    g = load(golden_dir, "threshold_map")
+    for tag in "abcdef":
+        u, q = T(g[f"{tag}_u"]), float(g[f"{tag}_q"])
+        thr, ranks, vals = O.quantile_linear_rows(u.flatten(1), q)
+        assert same(thr.numpy(), g[f"{tag}_thr"]), tag
+        kind = "higher" if bool(g[f"{tag}_higher"]) else "lower"
+        assert same(O.calculate_threshold_map(q, None, u, kind).numpy(), g[f"{tag}_mask"]), tag
+        # mask rebuilt from the restated threshold
+        thr_b = thr.view(-1, *([1] * (u.dim() - 1)))
+        m = (u > thr_b) if kind == "higher" else (u < thr_b)
+        assert same(m.float().numpy(), g[f"{tag}_mask"]), tag
+    assert same(O.calculate_threshold_map(T(g["t_thr"]), 2, T(g["t_u"]), "higher").numpy(), g["t_mask_hi"])
+    assert same(O.calculate_threshold_map(T(g["t_thr"]), 3, T(g["t_u"]), "lower").numpy(), g["t_mask_lo"])
+
+
+@pytest.mark.parametrize("n,q,lo,w", [(3072, .95, 2917, .44995), (12288, .9, 11058, .29980), (49152, .9, 44235, .8984375),
+                                      (16384, .9, 14744, .69921875), (4096, .95, 3890, .25)])
+def test_quantile_rank_known_answers(n, q, lo, w):
+    """SURVEY.md §8c known-answer facts, and bit-equality with torch.quantile on random rows."""
+    l, h, ww = O.quantile_rank(n, q)
+    assert l == lo and h == lo + 1 and abs(float(ww) - w) < 1e-4
+    x = torch.rand(3, n, generator=torch.Generator().manual_seed(n)) ** 2
+    thr, _, _ = O.quantile_linear_rows(x, q)
+    assert same(thr.numpy(), torch.quantile(x, q, dim=1).numpy())
+    assert int((x[0] > thr[0]).sum()) == n - 1 - lo  # tie-free row
+
+
+def test_quantile_edge_cases():
+    x = torch.rand(2, 7)
+    thr, _, _ = O.quantile_linear_rows(x, 0.5)
+    assert same(thr.numpy(), torch.quantile(x, 0.5, dim=1).numpy())
+    x[0, 3] = float("nan")
+    thr, _, _ = O.quantile_linear_rows(x, 0.5)
+    assert np.isnan(thr[0]) and not np.isnan(thr[1])
+    assert O.calculate_threshold_map(0.5, None, x, "higher")[0].sum() == 0  # NaN threshold -> all False
+    with pytest.raises(RuntimeError):
+        torch.quantile(torch.zeros(2, 8, dtype=torch.float16), 0.5, dim=1)
+    assert torch.isnan(O.variance_unbiased([torch.ones(3)])).all()  # M == 1
+    assert float(torch.var(torch.tensor([1.0, 2.0, 4.0]))) == pytest.approx(7.0 / 3.0)  # unbiased by default
+
+
+def test_posterior_update_matches_reference(golden_dir):
+    g = load(golden_dir, "posterior_update")
+    model = ToyADM(3, seed=11).eval()
+    x, y, eps = T(g["x"]), T(g["y"]), T(g["eps"])
+    t = int(g["t"]); M = int(g["M"]); a_hat = T(g["a_hat"])
+    t_tensor = torch.full((x.shape[0],), t, dtype=torch.long)
+    from math import sqrt
+    with torch.no_grad(), seeded_noise(11):
+        eps2 = model(x, t_tensor, y=y)[:, :3]
+        assert same(eps2.numpy(), eps.numpy())
+        # PU/...posterior_distribution.py:52-57: math.sqrt on a 0-dim tensor -> python float scalars
+        x0 = (x - sqrt(1 - a_hat) * eps) / sqrt(a_hat)
+        scores = []
+        for _ in range(M):
+            x_hat = sqrt(a_hat) * x0 + sqrt(1 - a_hat) * torch.randn_like(x)
+            scores.append(model(x_hat, t_tensor, y=y)[:, :3])
+    u = O.variance_with_center(scores, eps)
+    assert same(u.numpy(), g["u"])
+    mask = O.calculate_threshold_map(0.9, None, u, "higher")
+    assert same(mask.numpy(), g["mask"])
+    eps_new = O.posterior_blend(eps, u, mask, M, a_hat, sum_source=scores[-1], batch_sum=True)
+    # reference blends as post*mask + eps*(1-mask) (posterior_distribution.py:160); addition commutes
+    assert same(eps_new.numpy(), g["eps_new"])
+
+
+def test_sd_percentile_guidance_matches_reference(golden_dir):
+    from tests.toy_models import ToySDUNet
+    g = load(golden_dir, "sd_percentile_guidance")
+    sd = ToySDUNet(4, seed=12).eval()
+    lat, emb, a_hat = T(g["lat"]), T(g["emb"]), T(g["a_hat"])
+    lat2 = torch.cat([lat] * 2)
+    t_tensor = torch.tensor(int(g["t"]))
+    eps = T(g["post_eps"])
+    with torch.no_grad(), seeded_noise(12):
+        un, tx = sd(lat2, t_tensor, emb)[0].chunk(2)
+        assert same((un + 7.5 * (tx - un)).numpy(), eps.numpy())
+        x0 = (lat2 - torch.sqrt(1 - a_hat) * eps) / torch.sqrt(a_hat)   # uncertainty_guidance.py:86
+        scores = []
+        for _ in range(5):
+            x_hat = O.perturb_add_noise(x0, torch.randn_like(eps), a_hat)
+            un, tx = sd(x_hat, t_tensor, emb)[0].chunk(2)
+            scores.append(un + 7.5 * (tx - un))
+    u = O.variance_with_center(scores, eps)
+    mask = O.calculate_threshold_map(0.9, None, u, "higher")
+    out = O.posterior_blend(eps, u, mask, 5, a_hat, batch_sum=True)
+    assert same(out.numpy(), g["post_out"])
