@@ -1,0 +1,155 @@
+// du_common.cuh — shared device helpers for the sm_100a uncertainty-path kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/du_b200.h"
+
+namespace du {
+
+// ---- error plumbing (du_abi.cu) ----------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+#define DU_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return ::du::check_cuda(_e, #call); \
+  } while (0)
+#define DU_LAUNCH_CHECK(name) DU_CUDA(cudaPeekAtLastError())
+
+inline bool dtype_ok(int dt) { return dt == DU_F32 || dt == DU_F16 || dt == DU_BF16; }
+inline int dtype_size(int dt) { return dt == DU_F32 ? 4 : 2; }
+inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- scalar / vector loads with runtime dtype (warp-uniform switch) --------------------------------
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b16) { return __uint_as_float(b16 << 16); }
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+__device__ __forceinline__ float load1(const void* base, int64_t idx, int dt) {
+  if (dt == DU_F32) return __ldg(reinterpret_cast<const float*>(base) + idx);
+  uint16_t h = __ldg(reinterpret_cast<const uint16_t*>(base) + idx);
+  return dt == DU_F16 ? f16_bits_to_float(h) : bf16_bits_to_float(h);
+}
+
+__device__ __forceinline__ void store1(void* base, int64_t idx, int dt, float v) {
+  if (dt == DU_F32) reinterpret_cast<float*>(base)[idx] = v;
+  else if (dt == DU_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+}
+
+// streaming 128-bit load: read-only path, do not allocate in L1
+__device__ __forceinline__ uint4 ldg_stream_128(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_64(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// 4 consecutive elements starting at element index idx (idx % 4 == 0, pointer suitably aligned)
+__device__ __forceinline__ void load4(const void* base, int64_t idx, int dt, float (&v)[4]) {
+  if (dt == DU_F32) {
+    uint4 r = ldg_stream_128(reinterpret_cast<const float*>(base) + idx);
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  } else {
+    uint2 r = ldg_stream_64(reinterpret_cast<const uint16_t*>(base) + idx);
+    if (dt == DU_F16) {
+      v[0] = f16_bits_to_float(r.x & 0xffff); v[1] = f16_bits_to_float(r.x >> 16);
+      v[2] = f16_bits_to_float(r.y & 0xffff); v[3] = f16_bits_to_float(r.y >> 16);
+    } else {
+      v[0] = bf16_bits_to_float(r.x & 0xffff); v[1] = bf16_bits_to_float(r.x >> 16);
+      v[2] = bf16_bits_to_float(r.y & 0xffff); v[3] = bf16_bits_to_float(r.y >> 16);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void store4(void* base, int64_t idx, int dt, const float (&v)[4]) {
+  if (dt == DU_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if (dt == DU_F16) {
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = make_uint2(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]));
+  } else {
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+}
+
+// vector-path eligibility: every (pointer, stride) pair must keep 4-element groups aligned
+inline bool vec4_ok(const void* p, int64_t stride, int dt) {
+  if (p == nullptr) return true;
+  return aligned(p, 4 * (size_t)dtype_size(dt)) && (stride % 4 == 0);
+}
+
+// ---- order-preserving float <-> uint32 key ----------------------------------------------------------
+// -0.0 is canonicalised to +0.0 (torch's sort treats them as equal); NaNs are handled by the caller.
+__device__ __forceinline__ uint32_t float_to_key(float f) {
+  uint32_t b = __float_as_uint(f);
+  if ((b << 1) == 0) b = 0;
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(b);
+}
+
+// torch.lerp's two-branch formula (aten/native/Lerp.h).  fma = 0: one rounding per op (CPU kernel);
+// fma = 1: contracted like nvcc compiles torch's CUDA kernel.
+__device__ __forceinline__ float lerp_torch(float a, float b, float w, int fma) {
+  float diff = __fsub_rn(b, a);
+  if (fabsf(w) < 0.5f) return fma ? __fmaf_rn(w, diff, a) : __fadd_rn(a, __fmul_rn(w, diff));
+  float omw = __fsub_rn(1.0f, w);
+  return fma ? __fmaf_rn(-diff, omw, b) : __fsub_rn(b, __fmul_rn(diff, omw));
+}
+
+// ---- DDIM arithmetic: one IEEE rounding per reference operation (no FMA contraction) ----------------
+struct DdimOut { float prev, x0, eps; };
+
+__device__ __forceinline__ DdimOut ddim_update(float mo, float x, float noise, const du_ddim_coeffs& c) {
+  float x0, eps;
+  if (c.prediction_type == DU_PRED_EPSILON) {
+    x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.sqrt_beta_t, mo)), c.sqrt_alpha_t);
+    eps = mo;
+  } else if (c.prediction_type == DU_PRED_SAMPLE) {
+    x0 = mo;
+    eps = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.sqrt_alpha_t, x0)), c.sqrt_beta_t);
+  } else {
+    x0 = __fsub_rn(__fmul_rn(c.sqrt_alpha_t, x), __fmul_rn(c.sqrt_beta_t, mo));
+    eps = __fadd_rn(__fmul_rn(c.sqrt_alpha_t, mo), __fmul_rn(c.sqrt_beta_t, x));
+  }
+  if (c.clip_sample) {  // torch.clamp propagates NaN; fminf/fmaxf would swallow it
+    float cl = fminf(fmaxf(x0, -c.clip_range), c.clip_range);
+    x0 = (x0 != x0) ? x0 : cl;
+  }
+  if (c.use_clipped_model_output) eps = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.sqrt_alpha_t, x0)), c.sqrt_beta_t);
+  float prev = __fadd_rn(__fmul_rn(c.sqrt_alpha_prev, x0), __fmul_rn(c.dir_coef, eps));
+  if (c.add_noise) prev = __fadd_rn(prev, __fmul_rn(c.sigma, noise));
+  DdimOut o; o.prev = prev; o.x0 = x0; o.eps = eps;
+  return o;
+}
+
+// ---- launch geometry --------------------------------------------------------------------------------
+struct RowGrid { dim3 grid; dim3 block; };
+inline RowGrid row_grid(int64_t B, int64_t n_items_per_row, int threads) {
+  RowGrid g;
+  g.block = dim3(threads);
+  int64_t gx = (n_items_per_row + threads - 1) / threads;
+  if (gx < 1) gx = 1;
+  g.grid = dim3((unsigned)gx, (unsigned)(B < 65535 ? B : 65535));
+  return g;
+}
+
+}  // namespace du

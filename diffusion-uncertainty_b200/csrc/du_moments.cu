@@ -1,0 +1,288 @@
+// du_moments.cu — F1: single-pass reduction over the M axis.
+//
+// One thread owns VEC consecutive elements of one image and streams the M score tensors through
+// registers: every input byte is read exactly once with 128-bit, L1-bypassing loads, nothing is
+// stacked or staged.  Variance modes use the shifted-data form about the first sample
+// (d_m = x_m - x_0, exact or near-exact in fp32), so the accumulated quantities live on the scale
+// of the spread rather than the mean and the fp32 result stays within a few ulp of the
+// fp64-accumulated torch CPU value even when variance << mean^2.
+#include "du_common.cuh"
+
+namespace du {
+
+struct MomentsParams {
+  const void* scores[DU_MAX_M];
+  int M;
+  int mode;
+  int64_t score_stride;
+  const void* center;
+  int64_t center_stride;
+  int center_dtype;
+  int unc_dtype;
+  int64_t B, n;
+  void* unc;
+  int64_t unc_stride;
+  float* mean;
+  int64_t mean_stride;
+};
+
+template <typename T> struct ScoreVec;
+template <> struct ScoreVec<float> {
+  static constexpr int VEC = 4;
+  static constexpr int DT = DU_F32;
+  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[4]) {
+    uint4 r = ldg_stream_128(reinterpret_cast<const float*>(base) + idx);
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+};
+template <> struct ScoreVec<__half> {
+  static constexpr int VEC = 8;
+  static constexpr int DT = DU_F16;
+  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[8]) {
+    uint4 r = ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = f16_bits_to_float(w[i] & 0xffff); v[2 * i + 1] = f16_bits_to_float(w[i] >> 16); }
+  }
+};
+template <> struct ScoreVec<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  static constexpr int DT = DU_BF16;
+  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[8]) {
+    uint4 r = ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = bf16_bits_to_float(w[i] & 0xffff); v[2 * i + 1] = bf16_bits_to_float(w[i] >> 16); }
+  }
+};
+
+// Accumulator for one element.
+struct Acc {
+  float k;   // shift (first sample) for variance modes, centre for DU_MOM_CENTERED, 0 for RAW
+  float s1;  // sum of d
+  float s2;  // sum of d^2
+};
+
+__device__ __forceinline__ float finish(const Acc& a, int mode, bool centered, int count, float* mean_out) {
+  float cnt = (float)count;
+  if (mean_out) *mean_out = a.k + a.s1 / cnt;
+  if (mode == DU_MOM_CENTERED || mode == DU_MOM_RAW) return a.s2 / cnt;
+  if (mode == DU_MOM_PARTIAL_M2 && centered) return a.s2;
+  float m2 = a.s2 - a.s1 * a.s1 / cnt;  // sum of squared deviations about the mean (shifted-data form)
+  m2 = (m2 < 0.0f) ? 0.0f : m2;         // (NaN compares false and is kept)
+  if (mode == DU_MOM_PARTIAL_M2) return m2;
+  float var = m2 / (float)(count - 1);  // count == 1 -> 0/0 = NaN like torch.var
+  return mode == DU_MOM_STD_UNBIASED ? sqrtf(var) : var;
+}
+
+// kernel: grid.x covers a row in groups of VEC elements, grid.y strides over images.
+// VECTOR = false is the scalar fallback for unaligned / ragged views.
+template <typename T, bool VECTOR>
+__global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ MomentsParams p) {
+  using SV = ScoreVec<T>;
+  constexpr int VEC = VECTOR ? SV::VEC : 1;
+  const int64_t groups = (p.n + VEC - 1) / VEC;
+  const int mode = p.mode;
+  const bool centered = (mode == DU_MOM_CENTERED) || (mode == DU_MOM_PARTIAL_M2 && p.center != nullptr);
+  const bool shifted = !(centered || mode == DU_MOM_RAW);
+  const bool extra = (mode == DU_MOM_VAR_WITH_CENTER);
+
+  for (int64_t b = blockIdx.y; b < p.B; b += gridDim.y) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = g * VEC;
+      Acc acc[VEC];
+      float c[VEC];
+      if (p.center != nullptr) {
+        if constexpr (VECTOR) {
+          if (p.center_dtype == SV::DT) {
+            SV::load(p.center, b * p.center_stride + i, c);
+          } else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) c[e] = load1(p.center, b * p.center_stride + i + e, p.center_dtype);
+          }
+        } else {
+          c[0] = load1(p.center, b * p.center_stride + i, p.center_dtype);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { acc[e].k = centered ? c[e] : 0.0f; acc[e].s1 = 0.0f; acc[e].s2 = 0.0f; }
+
+      const int64_t off = b * p.score_stride + i;
+      int m = 0;
+      // chunks of 4 tensors: issue all loads of the chunk before consuming them (MLP)
+      for (; m + 4 <= p.M; m += 4) {
+        float x[4][VEC];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (VECTOR) SV::load(p.scores[m + j], off, x[j]);
+          else x[j][0] = load1(p.scores[m + j], off, SV::DT);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            if (shifted && m + j == 0) acc[e].k = x[j][e];
+            float d = x[j][e] - acc[e].k;
+            acc[e].s1 += d;
+            acc[e].s2 = fmaf(d, d, acc[e].s2);
+          }
+        }
+      }
+      for (; m < p.M; ++m) {
+        float x[VEC];
+        if constexpr (VECTOR) SV::load(p.scores[m], off, x);
+        else x[0] = load1(p.scores[m], off, SV::DT);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          if (shifted && m == 0) acc[e].k = x[e];
+          float d = x[e] - acc[e].k;
+          acc[e].s1 += d;
+          acc[e].s2 = fmaf(d, d, acc[e].s2);
+        }
+      }
+      if (extra) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float d = c[e] - acc[e].k;
+          acc[e].s1 += d;
+          acc[e].s2 = fmaf(d, d, acc[e].s2);
+        }
+      }
+      const int count = p.M + (extra ? 1 : 0);
+      float u[VEC], mu[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) u[e] = finish(acc[e], mode, centered, count, p.mean ? &mu[e] : nullptr);
+
+      if constexpr (VECTOR) {
+#pragma unroll
+        for (int h = 0; h < VEC / 4; ++h) {
+          float t4[4] = {u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]};
+          store4(p.unc, b * p.unc_stride + i + 4 * h, p.unc_dtype, t4);
+          if (p.mean) {
+            float m4[4] = {mu[4 * h], mu[4 * h + 1], mu[4 * h + 2], mu[4 * h + 3]};
+            store4(p.mean, b * p.mean_stride + i + 4 * h, DU_F32, m4);
+          }
+        }
+      } else {
+        store1(p.unc, b * p.unc_stride + i, p.unc_dtype, u[0]);
+        if (p.mean) p.mean[b * p.mean_stride + i] = mu[0];
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_moments(const MomentsParams& p, bool vec, cudaStream_t st) {
+  constexpr int VEC = ScoreVec<T>::VEC;
+  const int threads = 256;
+  int64_t groups = vec ? (p.n / VEC) : p.n;
+  RowGrid g = row_grid(p.B, groups, threads);
+  if (vec) moments_kernel<T, true><<<g.grid, g.block, 0, st>>>(p);
+  else moments_kernel<T, false><<<g.grid, g.block, 0, st>>>(p);
+  DU_LAUNCH_CHECK("moments_kernel");
+  return DU_OK;
+}
+
+// ---- Chan merge of per-rank partials -----------------------------------------------------------------
+struct MergeParams {
+  const float* means[DU_MAX_M];
+  const float* m2s[DU_MAX_M];
+  int counts[DU_MAX_M];
+  int R, mode;
+  int64_t N;
+  float* unc;
+  float* mean;
+};
+
+__global__ void __launch_bounds__(256) moments_merge_kernel(const __grid_constant__ MergeParams p) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.N; i += (int64_t)gridDim.x * blockDim.x) {
+    if (p.mode == DU_MOM_CENTERED) {
+      float s = 0.0f; int tot = 0;
+      for (int r = 0; r < p.R; ++r) { s += p.m2s[r][i]; tot += p.counts[r]; }
+      p.unc[i] = s / (float)tot;
+      continue;
+    }
+    // pairwise Chan update in rank order: M2 += M2_r + delta^2 * n_a n_r / (n_a + n_r)
+    float mean = p.means[0][i], m2 = p.m2s[0][i];
+    float na = (float)p.counts[0];
+    for (int r = 1; r < p.R; ++r) {
+      float nr = (float)p.counts[r];
+      if (nr == 0.0f) continue;
+      float delta = p.means[r][i] - mean;
+      float tot = na + nr;
+      m2 = m2 + p.m2s[r][i] + delta * delta * (na * nr / tot);
+      mean = mean + delta * (nr / tot);
+      na = tot;
+    }
+    float var = m2 / (na - 1.0f);
+    p.unc[i] = (p.mode == DU_MOM_STD_UNBIASED) ? sqrtf(var) : var;
+    if (p.mean) p.mean[i] = mean;
+  }
+}
+
+}  // namespace du
+
+using namespace du;
+
+extern "C" int du_moments(const void* const* scores, int M, int64_t score_stride, int score_dtype,
+                          const void* center, int64_t center_stride, int center_dtype, int mode,
+                          int64_t B, int64_t n, void* unc_out, int64_t unc_stride, int unc_dtype,
+                          float* mean_out, int64_t mean_stride, du_stream_t stream) {
+  if (!scores || M < 1 || M > DU_MAX_M) return set_error(DU_ERR_BAD_ARG, "du_moments: M=%d must be in [1,%d]", M, DU_MAX_M);
+  if (B < 0 || n < 0 || !unc_out) return set_error(DU_ERR_BAD_ARG, "du_moments: bad sizes or null output");
+  if (mode < DU_MOM_VAR_UNBIASED || mode > DU_MOM_PARTIAL_M2) return set_error(DU_ERR_BAD_ARG, "du_moments: bad mode %d", mode);
+  if (!dtype_ok(score_dtype) || !dtype_ok(unc_dtype) || (center && !dtype_ok(center_dtype)))
+    return set_error(DU_ERR_DTYPE, "du_moments: unsupported dtype");
+  if ((mode == DU_MOM_CENTERED || mode == DU_MOM_VAR_WITH_CENTER) && !center)
+    return set_error(DU_ERR_BAD_ARG, "du_moments: mode %d needs a centre tensor", mode);
+  if (mode == DU_MOM_VAR_UNBIASED || mode == DU_MOM_RAW || mode == DU_MOM_STD_UNBIASED) center = nullptr;
+  if (B == 0 || n == 0) return DU_OK;
+
+  MomentsParams p{};
+  const int es = dtype_size(score_dtype);
+  const int vec = (score_dtype == DU_F32) ? 4 : 8;
+  bool vec_ok = (n % vec == 0) && (score_stride % vec == 0);
+  for (int m = 0; m < M; ++m) {
+    if (!scores[m]) return set_error(DU_ERR_BAD_ARG, "du_moments: scores[%d] is null", m);
+    if (!aligned(scores[m], es)) return set_error(DU_ERR_ALIGN, "du_moments: scores[%d] misaligned", m);
+    p.scores[m] = scores[m];
+    vec_ok = vec_ok && aligned(scores[m], 16);
+  }
+  if (center) vec_ok = vec_ok && aligned(center, (size_t)vec * dtype_size(center_dtype)) && (center_stride % vec == 0);
+  vec_ok = vec_ok && aligned(unc_out, 4 * (size_t)dtype_size(unc_dtype)) && (unc_stride % 4 == 0);
+  if (mean_out) vec_ok = vec_ok && aligned(mean_out, 16) && (mean_stride % 4 == 0);
+  p.M = M; p.mode = mode; p.score_stride = score_stride;
+  p.center = center; p.center_stride = center_stride; p.center_dtype = center_dtype;
+  p.unc = unc_out; p.unc_stride = unc_stride; p.unc_dtype = unc_dtype;
+  p.mean = mean_out; p.mean_stride = mean_stride;
+  p.B = B; p.n = n;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (score_dtype) {
+    case DU_F32: return launch_moments<float>(p, vec_ok, st);
+    case DU_F16: return launch_moments<__half>(p, vec_ok, st);
+    default: return launch_moments<__nv_bfloat16>(p, vec_ok, st);
+  }
+}
+
+extern "C" int du_moments_merge(const float* const* means, const float* const* m2s, const int* counts, int R,
+                                int mode, int64_t N, float* unc_out, float* mean_out, du_stream_t stream) {
+  if (R < 1 || R > DU_MAX_M || !m2s || !counts || !unc_out || N < 0)
+    return set_error(DU_ERR_BAD_ARG, "du_moments_merge: bad arguments (R=%d)", R);
+  if (mode != DU_MOM_CENTERED && mode != DU_MOM_VAR_UNBIASED && mode != DU_MOM_STD_UNBIASED)
+    return set_error(DU_ERR_BAD_ARG, "du_moments_merge: bad mode %d", mode);
+  if (mode != DU_MOM_CENTERED && !means) return set_error(DU_ERR_BAD_ARG, "du_moments_merge: means required");
+  if (N == 0) return DU_OK;
+  MergeParams p{};
+  for (int r = 0; r < R; ++r) {
+    p.means[r] = means ? means[r] : nullptr;
+    p.m2s[r] = m2s[r];
+    p.counts[r] = counts[r];
+  }
+  p.R = R; p.mode = mode; p.N = N; p.unc = unc_out; p.mean = mean_out;
+  int threads = 256;
+  int64_t blocks = (N + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  moments_merge_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(p);
+  DU_LAUNCH_CHECK("moments_merge_kernel");
+  return DU_OK;
+}

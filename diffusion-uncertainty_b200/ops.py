@@ -1,0 +1,365 @@
+"""Tensor-level wrappers over the C ABI (include/du_b200.h).  PyTorch is plumbing only here: it owns the
+device memory and the stream; every arithmetic step of the path runs in libdu_b200.so.
+
+All functions require CUDA tensors — there is no CPU fallback (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.float16: L.F16, torch.bfloat16: L.BF16}
+_MODES = {"var": L.MOM_VAR_UNBIASED, "centered": L.MOM_CENTERED, "var_with_center": L.MOM_VAR_WITH_CENTER,
+          "raw": L.MOM_RAW, "std": L.MOM_STD_UNBIASED, "partial": L.MOM_PARTIAL_M2}
+_PRED = {"epsilon": L.PRED_EPSILON, "sample": L.PRED_SAMPLE, "v_prediction": L.PRED_V}
+_GUIDE = {"none": L.GUIDE_NONE, "posterior": L.GUIDE_POSTERIOR, "grad_blend": L.GUIDE_GRAD_BLEND,
+          "grad_add": L.GUIDE_GRAD_ADD, "weights": L.GUIDE_WEIGHTS}
+_ZN = {"max": L.ZN_BELOW, "min": L.ZN_ABOVE, "below": L.ZN_BELOW, "above": L.ZN_ABOVE, "multiscale": L.ZN_MULTISCALE}
+
+# launches issued through this module since import (bench.py reports it as gpu_launches)
+launch_count = 0
+_current_device = [None]
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the uncertainty path has no CPU fallback, move it to a CUDA device")
+    if t.dtype not in _DT:
+        raise RuntimeError(f"{name}: dtype {t.dtype} is not supported (float32, float16, bfloat16)")
+
+
+def _stream(t: torch.Tensor):
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if _current_device[0] != idx:
+        L.check(L.load().du_set_device(idx))
+        _current_device[0] = idx
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class Rows:
+    """A tensor seen as B rows of n contiguous elements (the C ABI's 'rows view')."""
+    __slots__ = ("t", "ptr", "stride", "dt", "B", "n")
+
+    def __init__(self, t: torch.Tensor, name: str = "tensor", batch: bool = True):
+        _require_cuda(t, name)
+        if t.dim() == 0:
+            t = t.reshape(1, 1)
+        if not batch:
+            t = t.reshape(1, -1) if t.is_contiguous() else t.contiguous().reshape(1, -1)
+        B = t.shape[0]
+        n = t.numel() // B if B > 0 else 0
+        # rows must be internally contiguous; the batch stride may be anything (channel-slice views)
+        if B > 0 and n > 0 and not t[0].is_contiguous():
+            t = t.contiguous()
+        self.t = t
+        self.ptr = C.c_void_p(t.data_ptr())
+        self.stride = t.stride(0) if (B > 1 and t.dim() > 0) else n
+        self.dt = _DT[t.dtype]
+        self.B, self.n = B, n
+
+
+def _same_rows(a: Rows, b: Rows, what: str):
+    if a.B != b.B or a.n != b.n:
+        raise ValueError(f"{what}: shape mismatch ({a.B}x{a.n} vs {b.B}x{b.n})")
+
+
+NULL = C.c_void_p(0)
+
+
+# ------------------------------------------------------------------------------------------------ F1
+def moments(scores: Union[Sequence[torch.Tensor], torch.Tensor], center: Optional[torch.Tensor] = None,
+            mode: str = "var", out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+            return_mean: bool = False):
+    """Reduce M score tensors [B,...] over the M axis without stacking them (du_moments).
+    mode: 'var' | 'centered' | 'var_with_center' | 'raw' | 'std' | 'partial'.
+    `out` may be a (strided) slot view of the accumulation buffer."""
+    if isinstance(scores, torch.Tensor):
+        scores = list(scores.unbind(0))
+    if len(scores) == 0:
+        raise ValueError("moments: need at least one score tensor")
+    if len(scores) > L.DU_MAX_M:
+        raise ValueError(f"moments: M={len(scores)} exceeds DU_MAX_M={L.DU_MAX_M}")
+    rows = [Rows(s, f"scores[{k}]") for k, s in enumerate(scores)]
+    r0 = rows[0]
+    for r in rows[1:]:
+        _same_rows(r0, r, "moments")
+        if r.dt != r0.dt:
+            raise RuntimeError("moments: all score tensors must share one dtype")
+    strides = {r.stride for r in rows}
+    if len(strides) != 1:  # mixed layouts: normalise
+        rows = [Rows(r.t.contiguous(), "scores") for r in rows]
+        r0 = rows[0]
+    shape = scores[0].shape
+    crow = None
+    if center is not None:
+        crow = Rows(center, "center")
+        _same_rows(r0, crow, "moments(center)")
+    if out is None:
+        out = torch.empty(shape, device=scores[0].device, dtype=out_dtype or torch.float32)
+    orow = Rows(out, "out")
+    if orow.t is not out:
+        raise ValueError("moments: `out` rows must be contiguous")
+    _same_rows(r0, orow, "moments(out)")
+    mean = torch.empty(shape, device=scores[0].device, dtype=torch.float32) if return_mean else None
+    ptrs = (C.c_void_p * len(rows))(*[r.ptr for r in rows])
+    rc = L.load().du_moments(ptrs, len(rows), r0.stride, r0.dt,
+                             crow.ptr if crow else NULL, crow.stride if crow else 0, crow.dt if crow else 0,
+                             _MODES[mode], r0.B, r0.n, orow.ptr, orow.stride, orow.dt,
+                             C.c_void_p(mean.data_ptr()) if mean is not None else NULL, r0.n, _stream(out))
+    L.check(rc)
+    _count()
+    return (out, mean) if return_mean else out
+
+
+def moments_merge(means: Sequence[torch.Tensor], m2s: Sequence[torch.Tensor], counts: Sequence[int], mode: str = "var",
+                  return_mean: bool = False):
+    """Chan-merge R per-rank partial moments (du_moments_merge)."""
+    R = len(m2s)
+    m2s = [m.contiguous() for m in m2s]
+    for m in m2s:
+        _require_cuda(m, "m2")
+    N = m2s[0].numel()
+    out = torch.empty_like(m2s[0], dtype=torch.float32)
+    mean_out = torch.empty_like(out) if return_mean else None
+    mp = None
+    if mode != "centered":
+        means = [m.contiguous() for m in means]
+        mp = (C.c_void_p * R)(*[C.c_void_p(m.data_ptr()) for m in means])
+    qp = (C.c_void_p * R)(*[C.c_void_p(m.data_ptr()) for m in m2s])
+    cp = (C.c_int * R)(*[int(c) for c in counts])
+    rc = L.load().du_moments_merge(mp, qp, cp, R, _MODES[mode], N, C.c_void_p(out.data_ptr()),
+                                   C.c_void_p(mean_out.data_ptr()) if return_mean else NULL, _stream(out))
+    L.check(rc)
+    _count()
+    return (out, mean_out) if return_mean else out
+
+
+# ------------------------------------------------------------------------------------------------ F2
+def quantile_threshold(u: torch.Tensor, q: float, lerp_fma: bool = False, return_details: bool = False):
+    """Per-image threshold == torch.quantile(u.flatten(1).float(), q, dim=1), bit for bit (du_quantile_threshold)."""
+    _require_cuda(u, "u")
+    if u.dtype != torch.float32:
+        u = u.to(torch.float32)  # the reference casts too (posterior_distribution.py:15)
+    r = Rows(u, "u")
+    thr = torch.empty(r.B, device=u.device, dtype=torch.float32)
+    ranks = torch.empty((r.B, 2), device=u.device, dtype=torch.int32) if return_details else None
+    vals = torch.empty((r.B, 2), device=u.device, dtype=torch.float32) if return_details else None
+    lib = L.load()
+    nbytes = lib.du_quantile_scratch_bytes(r.B, r.n)
+    scratch = torch.empty(max(int(nbytes), 16), device=u.device, dtype=torch.uint8)
+    rc = lib.du_quantile_threshold(r.ptr, r.B, r.n, r.stride, float(q), int(bool(lerp_fma)), C.c_void_p(thr.data_ptr()),
+                                   C.c_void_p(ranks.data_ptr()) if return_details else NULL,
+                                   C.c_void_p(vals.data_ptr()) if return_details else NULL,
+                                   C.c_void_p(scratch.data_ptr()), scratch.numel(), _stream(u))
+    if rc == -4 or (rc == -1 and "quantile()" in lib.du_last_error().decode()):
+        raise RuntimeError(lib.du_last_error().decode())  # torch.quantile raises RuntimeError for these
+    L.check(rc)
+    _count()
+    return (thr, ranks, vals) if return_details else thr
+
+
+def threshold_mask(u: torch.Tensor, thr: torch.Tensor, higher: bool = True) -> torch.Tensor:
+    r = Rows(u, "u")
+    _require_cuda(thr, "thr")
+    thr = thr.reshape(-1).to(torch.float32).contiguous()
+    if thr.numel() != r.B:
+        raise ValueError("threshold_mask: one threshold per image expected")
+    mask = torch.empty(u.shape, device=u.device, dtype=torch.float32)
+    rc = L.load().du_threshold_mask(r.ptr, r.stride, r.dt, C.c_void_p(thr.data_ptr()), int(higher), r.B, r.n,
+                                    C.c_void_p(mask.data_ptr()), r.n, _stream(u))
+    L.check(rc)
+    _count()
+    return mask
+
+
+def tensor_threshold_mask(u: torch.Tensor, thr_map: torch.Tensor, higher: bool = True) -> torch.Tensor:
+    r = Rows(u, "u")
+    t = Rows(thr_map, "threshold", batch=False)
+    if t.n != r.n:
+        raise ValueError(f"tensor threshold has {t.n} elements per image, map has {r.n}")
+    mask = torch.empty(u.shape, device=u.device, dtype=torch.float32)
+    rc = L.load().du_tensor_threshold_mask(r.ptr, r.stride, r.dt, t.ptr, t.dt, int(higher), r.B, r.n,
+                                           C.c_void_p(mask.data_ptr()), r.n, _stream(u))
+    L.check(rc)
+    _count()
+    return mask
+
+
+def znorm_stats(u: torch.Tensor) -> torch.Tensor:
+    """Device tensor [mean, unbiased std, count, M2] over ALL elements of u (du_znorm_stats)."""
+    r = Rows(u, "u")
+    lib = L.load()
+    stats = torch.empty(4, device=u.device, dtype=torch.float32)
+    nbytes = int(lib.du_znorm_scratch_bytes(r.B, r.n))
+    scratch = torch.empty(max(nbytes // 8, 2), device=u.device, dtype=torch.float64)
+    rc = lib.du_znorm_stats(r.ptr, r.stride, r.dt, r.B, r.n, C.c_void_p(stats.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                            scratch.numel() * 8, _stream(u))
+    L.check(rc)
+    _count(2)
+    return stats
+
+
+def znorm_stats_combine(stats_blocks: torch.Tensor) -> torch.Tensor:
+    _require_cuda(stats_blocks, "stats")
+    s = stats_blocks.reshape(-1, 4).to(torch.float32).contiguous()
+    out = torch.empty(4, device=s.device, dtype=torch.float32)
+    L.check(L.load().du_znorm_stats_combine(C.c_void_p(s.data_ptr()), s.shape[0], C.c_void_p(out.data_ptr()), _stream(s)))
+    _count()
+    return out
+
+
+def znorm_weights(u: torch.Tensor, stats: Optional[torch.Tensor], mode: str = "max", thr: float = 1.0, normalize: bool = True,
+                  want_z: bool = True, want_w: bool = True):
+    r = Rows(u, "u")
+    z = torch.empty(u.shape, device=u.device, dtype=torch.float32) if want_z else None
+    w = torch.empty(u.shape, device=u.device, dtype=torch.float32) if want_w else None
+    rc = L.load().du_znorm_weights(r.ptr, r.stride, r.dt, C.c_void_p(stats.data_ptr()) if stats is not None else NULL,
+                                   int(normalize), _ZN[mode], float(thr), r.B, r.n,
+                                   C.c_void_p(z.data_ptr()) if want_z else NULL, r.n,
+                                   C.c_void_p(w.data_ptr()) if want_w else NULL, r.n, _stream(u))
+    L.check(rc)
+    _count()
+    return z, w
+
+
+# ------------------------------------------------------------------------------------------------ F3
+def make_coeffs(sqrt_alpha_t, sqrt_beta_t, sqrt_alpha_prev, dir_coef, sigma=0.0, clip_sample=True, clip_range=1.0,
+                prediction_type="epsilon", use_clipped_model_output=False, add_noise=False) -> L.DdimCoeffs:
+    if prediction_type not in _PRED:
+        raise ValueError(f"prediction_type given as {prediction_type} must be one of `epsilon`, `sample`, or `v_prediction`")
+    return L.DdimCoeffs(float(sqrt_alpha_t), float(sqrt_beta_t), float(sqrt_alpha_prev), float(dir_coef), float(sigma),
+                        float(clip_range), _PRED[prediction_type], int(bool(clip_sample)),
+                        int(bool(use_clipped_model_output)), int(bool(add_noise)))
+
+
+def ddim_step(model_output: torch.Tensor, sample: torch.Tensor, coeffs: L.DdimCoeffs, noise: Optional[torch.Tensor] = None,
+              want_prev: bool = True, want_x0: bool = True, want_eps: bool = False):
+    """x_{t-1}, x0 (and eps) in one pass (du_ddim_step).  Outputs take sample's dtype promoted with fp32 scalars,
+    i.e. sample.dtype, like the reference's eager expressions."""
+    mo, s = Rows(model_output, "model_output"), Rows(sample, "sample")
+    _same_rows(mo, s, "ddim_step")
+    out_dtype = torch.promote_types(model_output.dtype, sample.dtype)
+    nz = None
+    if coeffs.add_noise:
+        if noise is None:
+            raise ValueError("ddim_step: eta > 0 needs a noise tensor")
+        nz = Rows(noise, "noise")
+        _same_rows(mo, nz, "ddim_step(noise)")
+    mk = lambda want: torch.empty(sample.shape, device=sample.device, dtype=out_dtype) if want else None  # noqa: E731
+    prev, x0, eps = mk(want_prev), mk(want_x0), mk(want_eps)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else NULL  # noqa: E731
+    od = _DT[out_dtype]
+    rc = L.load().du_ddim_step(mo.ptr, mo.stride, mo.dt, s.ptr, s.stride, s.dt, nz.ptr if nz else NULL, nz.stride if nz else 0,
+                               nz.dt if nz else 0, C.byref(coeffs), mo.B, mo.n, p(prev), mo.n, od, p(x0), mo.n, od, p(eps), mo.n, od,
+                               _stream(sample))
+    L.check(rc)
+    _count()
+    return prev, x0, eps
+
+
+def guided_step(eps: torch.Tensor, sample: Optional[torch.Tensor], coeffs: Optional[L.DdimCoeffs], guidance: str = "none",
+                u: Optional[torch.Tensor] = None, thr: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+                aux: Optional[torch.Tensor] = None, aux_broadcast: bool = False, higher: bool = True, lam: float = 1.0,
+                post_M: float = 0.0, inv_alpha_hat: float = 0.0, want_prev: bool = True, want_x0: bool = False,
+                want_eps: bool = True, want_mask: bool = False):
+    """mask + guided score + DDIM update in one elementwise pass (du_guided_step).
+    Returns dict(prev, x0, eps, mask) with None for outputs not requested."""
+    e = Rows(eps, "eps")
+    P = L.GuidedParams()
+    P.eps, P.eps_stride, P.eps_dtype, P.guidance = e.ptr, e.stride, e.dt, _GUIDE[guidance]
+    keep = [e]
+    skip = sample is None
+    out_dtype = eps.dtype if skip else torch.promote_types(eps.dtype, sample.dtype)
+    if u is not None or mask is not None or aux is not None:
+        out_dtype = torch.promote_types(out_dtype, torch.float32)
+    if not skip:
+        s = Rows(sample, "sample"); _same_rows(e, s, "guided_step(sample)"); keep.append(s)
+        P.sample, P.sample_stride, P.sample_dtype = s.ptr, s.stride, s.dt
+        P.ddim = coeffs
+    P.skip_ddim = int(skip)
+    P.higher = int(higher)
+    if u is not None:
+        if u.dtype != torch.float32:
+            u = u.float()
+        ur = Rows(u, "u"); _same_rows(e, ur, "guided_step(u)"); keep.append(ur)
+        P.u, P.u_stride = ur.ptr, ur.stride
+    if thr is not None:
+        _require_cuda(thr, "thr")
+        thr = thr.reshape(-1).to(torch.float32).contiguous(); keep.append(thr)
+        if thr.numel() != e.B:
+            raise ValueError("guided_step: one threshold per image expected")
+        P.thr = C.c_void_p(thr.data_ptr())
+    if mask is not None:
+        if mask.dtype != torch.float32:
+            mask = mask.float()
+        mr = Rows(mask, "mask"); _same_rows(e, mr, "guided_step(mask)"); keep.append(mr)
+        P.mask, P.mask_stride = mr.ptr, mr.stride
+    if aux is not None:
+        ar = Rows(aux, "aux", batch=not aux_broadcast); keep.append(ar)
+        if ar.n != e.n:
+            raise ValueError("guided_step: aux has the wrong number of elements per image")
+        P.aux, P.aux_stride, P.aux_dtype, P.aux_broadcast = ar.ptr, ar.stride, ar.dt, int(aux_broadcast)
+    P.lam, P.post_M, P.inv_alpha_hat = float(lam), float(post_M), float(inv_alpha_hat)
+    P.B, P.n = e.B, e.n
+    shape, dev = eps.shape, eps.device
+    res = {"prev": None, "x0": None, "eps": None, "mask": None}
+    od = _DT[out_dtype]
+    if want_prev and not skip:
+        res["prev"] = torch.empty(shape, device=dev, dtype=out_dtype)
+        P.prev_out, P.prev_stride, P.prev_dtype = C.c_void_p(res["prev"].data_ptr()), e.n, od
+    if want_x0 and not skip:
+        res["x0"] = torch.empty(shape, device=dev, dtype=out_dtype)
+        P.x0_out, P.x0_stride, P.x0_dtype = C.c_void_p(res["x0"].data_ptr()), e.n, od
+    if want_eps:
+        res["eps"] = torch.empty(shape, device=dev, dtype=out_dtype)
+        P.eps_out, P.eps_out_stride, P.eps_out_dtype = C.c_void_p(res["eps"].data_ptr()), e.n, od
+    if want_mask:
+        res["mask"] = torch.empty(shape, device=dev, dtype=torch.float32)
+        P.mask_out, P.mask_out_stride = C.c_void_p(res["mask"].data_ptr()), e.n
+    L.check(L.load().du_guided_step(C.byref(P), _stream(eps)))
+    _count()
+    del keep
+    return res
+
+
+def batch_sum(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(dim=0) as fp32 (du_batch_sum) — the reference's batch-axis sum of the posterior score."""
+    r = Rows(x, "x")
+    out = torch.empty(x.shape[1:], device=x.device, dtype=torch.float32)
+    L.check(L.load().du_batch_sum(r.ptr, r.stride, r.dt, r.B, r.n, C.c_void_p(out.data_ptr()), _stream(x)))
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ F7 / F8
+def perturb(x: torch.Tensor, noise: torch.Tensor, a: float, b: float, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """a*x + b*noise (du_perturb)."""
+    xr, nr = Rows(x, "x"), Rows(noise, "noise")
+    _same_rows(xr, nr, "perturb")
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or torch.promote_types(x.dtype, noise.dtype))
+    rc = L.load().du_perturb(xr.ptr, xr.stride, xr.dt, nr.ptr, nr.stride, nr.dt, float(a), float(b), xr.B, xr.n,
+                             C.c_void_p(out.data_ptr()), xr.n, _DT[out.dtype], _stream(x))
+    L.check(rc)
+    _count()
+    return out
+
+
+def accumulate_slot(src: torch.Tensor, dst_slot: torch.Tensor):
+    """Copy/convert one step's map into its slot view buffer[:, t] (du_accumulate_slot)."""
+    s, d = Rows(src, "src"), Rows(dst_slot, "dst")
+    if d.t is not dst_slot:
+        raise ValueError("accumulate_slot: destination rows must be contiguous")
+    _same_rows(s, d, "accumulate_slot")
+    L.check(L.load().du_accumulate_slot(s.ptr, s.stride, s.dt, s.B, s.n, d.ptr, d.stride, d.dt, _stream(src)))
+    _count()

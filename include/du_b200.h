@@ -1,0 +1,257 @@
+/* du_b200.h — C ABI of the B200-native per-step uncertainty path of diffusion-uncertainty.
+ *
+ * The reference (Michedev/diffusion-uncertainty) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md §8b); this header IS the drop-in boundary.  Every entry point replaces a group of eager
+ * ATen expressions of the reference, cited per function as file:line relative to
+ * /root/reference/diffusion_uncertainty/ (SU = schedulers_uncertainty, PU = pipeline_uncertainty).
+ * The reference-side binding (the ctypes stub a maintainer would add) is in INTEGRATION.md; the
+ * Python host layer that mirrors the reference's scheduler/pipeline API on top of this ABI is
+ * diffusion-uncertainty_b200/.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  All data pointers are DEVICE pointers owned by the caller (torch
+ *    allocations); the library never allocates user-visible memory and never synchronises the device.
+ *  - A tensor is passed as a "rows view": B rows of n contiguous elements, row b starting
+ *    `stride` ELEMENTS after row b-1.  This covers contiguous [B,C,H,W] tensors (stride = n), the
+ *    ADM `model(...)[:, :3]` channel-slice view (stride = 6*H*W, n = 3*H*W) and a slot
+ *    [:, t] of the [B,T_uc,C,H,W] accumulation buffer (stride = T_uc*n).
+ *  - dtype codes: du_dtype.  Arithmetic is always fp32 (fp64 for the few global sums).
+ *  - Every function is asynchronous on `stream` (a cudaStream_t), re-entrant, CUDA-graph capturable
+ *    (no host reads of device results), and returns DU_OK or a negative du_status;
+ *    du_last_error() gives the thread-local message.
+ *  - No CPU fallback exists.
+ */
+#ifndef DU_B200_H
+#define DU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* du_stream_t; /* cudaStream_t */
+
+enum du_dtype { DU_F32 = 0, DU_F16 = 1, DU_BF16 = 2 };
+
+enum du_status {
+  DU_OK = 0,
+  DU_ERR_BAD_ARG = -1,   /* null pointer, negative size, q outside [0,1], ...  -> ValueError      */
+  DU_ERR_DTYPE = -2,     /* unsupported dtype code                             -> RuntimeError    */
+  DU_ERR_ALIGN = -3,     /* pointer not aligned to its element size            -> RuntimeError    */
+  DU_ERR_TOO_LARGE = -4, /* quantile row longer than 2^24 (torch.quantile's own limit)            */
+  DU_ERR_CUDA = -5,      /* a CUDA runtime call failed (message in du_last_error)                 */
+  DU_ERR_SCRATCH = -6    /* scratch buffer too small                                               */
+};
+
+#define DU_MAX_M 64 /* maximum number of score tensors reduced by one du_moments call */
+
+const char* du_last_error(void);
+int du_version(void);            /* ABI version, currently 1 */
+int du_num_sms(int device);      /* SM count of `device` (148 on B200); <0 on error */
+int du_set_device(int device);   /* make `device` current for this thread's subsequent calls (one process per GPU) */
+
+/* ------------------------------------------------------------------------------------------------
+ * F1 — reduction over the M axis.
+ * Replaces torch.stack(scores,0) followed by
+ *   DU_MOM_VAR_UNBIASED       torch.var(., dim=0)                SU/scheduling_ddim_mc_dropout.py:506,
+ *                             SU/scheduling_ddim_uncertainty_threshold.py:537, generate_samples.py:815
+ *   DU_MOM_CENTERED           (. - eps[None]).pow(2).mean(0)     SU/scheduling_ddim_uncertainty_zigzag_centered.py:549
+ *   DU_MOM_VAR_WITH_CENTER    torch.var(stack(scores+[eps]),0)   uncertainty_guidance.py:101-106,
+ *                             PU/pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution.py:58-61
+ *   DU_MOM_RAW                .pow(2).mean(0)                    uncertainty_guidance.py:48
+ *   DU_MOM_STD_UNBIASED       .std(0)                            generate_samples.py:941
+ * scores: HOST array of M device pointers (M <= DU_MAX_M), all of dtype score_dtype and row stride
+ * score_stride.  center may be NULL unless the mode needs it.  mean_out (fp32, nullable) receives
+ * the mean over the samples the mode reduces (M, or M+1 for VAR_WITH_CENTER).  unc_out may be a slot
+ * of the accumulation buffer (F8 fused: generate_samples.py:192-201).
+ * ---------------------------------------------------------------------------------------------- */
+enum du_moments_mode {
+  DU_MOM_VAR_UNBIASED = 0,
+  DU_MOM_CENTERED = 1,
+  DU_MOM_VAR_WITH_CENTER = 2,
+  DU_MOM_RAW = 3,
+  DU_MOM_STD_UNBIASED = 4,
+  /* partial results for M-sharding across GPUs: unc_out = sum of squared deviations
+   * about the LOCAL mean (or about `center` when center != NULL), mean_out = local mean */
+  DU_MOM_PARTIAL_M2 = 5
+};
+
+int du_moments(const void* const* scores, int M, int64_t score_stride, int score_dtype,
+               const void* center, int64_t center_stride, int center_dtype, int mode,
+               int64_t B, int64_t n,
+               void* unc_out, int64_t unc_stride, int unc_dtype,
+               float* mean_out, int64_t mean_stride, du_stream_t stream);
+
+/* Chan merge of R per-rank partials (after an all-gather) into the final map.
+ * means[r], m2s[r]: device pointers to contiguous [B*n] fp32 (from DU_MOM_PARTIAL_M2); counts[r] =
+ * samples reduced on rank r.  mode: DU_MOM_VAR_UNBIASED / DU_MOM_STD_UNBIASED (divide by total-1) or
+ * DU_MOM_CENTERED (m2s are sums about the common centre: plain sum / total; means may be NULL). */
+int du_moments_merge(const float* const* means, const float* const* m2s, const int* counts, int R,
+                     int mode, int64_t N, float* unc_out, float* mean_out, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F2a — per-row linear-interpolated quantile, bit-identical to
+ *   torch.quantile(u.flatten(1).to(float32), q, dim=1)
+ * PU/...posterior_distribution.py:15, uncertainty_guidance.py:112, generate_samples.py:946.
+ * rank = fp32(q)*fp32(n-1); lo = floor, hi = ceil; thr = lerp(sorted[lo], sorted[hi], rank-lo) with
+ * torch's two-branch lerp.  lerp_fma = 0 reproduces torch's CPU kernel (separate mul/add),
+ * 1 reproduces torch's CUDA kernel (contracted to FMA).  A row containing NaN yields NaN.
+ * thr_out[B]; rank_out[B][2] (nullable) = {lo, hi}; val_out[B][2] (nullable) = the two order
+ * statistics.  scratch: du_quantile_scratch_bytes(B, n) bytes of device memory.
+ * ---------------------------------------------------------------------------------------------- */
+size_t du_quantile_scratch_bytes(int64_t B, int64_t n);
+int du_quantile_threshold(const float* u, int64_t B, int64_t n, int64_t stride, float q, int lerp_fma,
+                          float* thr_out, int32_t* rank_out, float* val_out,
+                          void* scratch, size_t scratch_bytes, du_stream_t stream);
+
+/* mask = (u > thr[b]) (higher != 0) or (u < thr[b]), strict, as fp32 0/1.
+ * PU/...posterior_distribution.py:16-20. */
+int du_threshold_mask(const void* u, int64_t u_stride, int u_dtype, const float* thr, int higher,
+                      int64_t B, int64_t n, float* mask_out, int64_t mask_stride, du_stream_t stream);
+
+/* F2b — mask = (u > thr_map) with thr_map one row of n elements broadcast over the batch
+ * (threshold[i].unsqueeze(0)).  PU/...posterior_distribution.py:21-29, generate_samples.py:819. */
+int du_tensor_threshold_mask(const void* u, int64_t u_stride, int u_dtype, const void* thr_map,
+                             int thr_dtype, int higher, int64_t B, int64_t n, float* mask_out,
+                             int64_t mask_stride, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F2c — whole-batch z-normalisation statistics: stats_out[0] = mean, [1] = unbiased std,
+ * [2] = count, [3] = sum of squared deviations (fp32, device).  Deterministic (fixed merge order).
+ * SU/scheduling_ddim_uncertainty_threshold.py:539-540.
+ * du_znorm_stats_merge rescales stats after the per-rank (count, mean, M2) triples were all-reduced
+ * is not needed: pass R gathered stat blocks to du_znorm_stats_combine.
+ * ---------------------------------------------------------------------------------------------- */
+size_t du_znorm_scratch_bytes(int64_t B, int64_t n);
+int du_znorm_stats(const void* u, int64_t u_stride, int u_dtype, int64_t B, int64_t n, float* stats_out,
+                   void* scratch, size_t scratch_bytes, du_stream_t stream);
+/* Chan merge of R stats blocks ([R][4], device, e.g. after an all-gather over ranks) into one. */
+int du_znorm_stats_combine(const float* stats_in, int R, float* stats_out, du_stream_t stream);
+
+enum du_znorm_mode { DU_ZN_BELOW = 0 /* 'max': z < thr */, DU_ZN_ABOVE = 1 /* z > thr */, DU_ZN_MULTISCALE = 2 };
+/* z = normalize ? (u-mean)/std : u;  weights per mode (multiscale: 0.8 / 0.9 / 1.0 bands,
+ * SU/scheduling_ddim_infer_noise_multiscale_threshold.py:538-548).  z_out / w_out nullable. */
+int du_znorm_weights(const void* u, int64_t u_stride, int u_dtype, const float* stats, int normalize,
+                     int mode, float thr, int64_t B, int64_t n, float* z_out, int64_t z_stride,
+                     float* w_out, int64_t w_stride, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F3 — DDIM / DDPM-variance x_{t-1} update.  SU/scheduling_ddim_uncertainty_zigzag_centered.py:472-525.
+ * The host computes the scalars with the reference's own fp32 expressions (:462-468, 294-302, 507).
+ * ---------------------------------------------------------------------------------------------- */
+enum du_prediction_type { DU_PRED_EPSILON = 0, DU_PRED_SAMPLE = 1, DU_PRED_V = 2 };
+
+typedef struct du_ddim_coeffs {
+  float sqrt_alpha_t;     /* alpha_prod_t ** 0.5                       */
+  float sqrt_beta_t;      /* (1 - alpha_prod_t) ** 0.5                 */
+  float sqrt_alpha_prev;  /* alpha_prod_t_prev ** 0.5                  */
+  float dir_coef;         /* (1 - alpha_prod_t_prev - std_dev_t**2) ** 0.5 */
+  float sigma;            /* std_dev_t = eta * variance ** 0.5         */
+  float clip_range;       /* clip_sample_range                         */
+  int32_t prediction_type;
+  int32_t clip_sample;
+  int32_t use_clipped_model_output;
+  int32_t add_noise;      /* eta > 0: prev += sigma * noise            */
+} du_ddim_coeffs;
+
+/* prev_out / x0_out / eps_out are nullable (at least one must be given).  noise required iff add_noise. */
+int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_dtype,
+                 const void* sample, int64_t s_stride, int s_dtype,
+                 const void* noise, int64_t noise_stride, int noise_dtype,
+                 const du_ddim_coeffs* c, int64_t B, int64_t n,
+                 void* prev_out, int64_t prev_stride, int prev_dtype,
+                 void* x0_out, int64_t x0_stride, int x0_dtype,
+                 void* eps_out, int64_t eps_stride, int eps_dtype, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F2 (mask) + F4/F5/F6 (guided score) + F3 (DDIM) in ONE elementwise pass.
+ *   guidance   reference                                                      eps' =
+ *   POSTERIOR  uncertainty_guidance.py:115-120; PU/...posterior_distribution.py:63-68,160
+ *                                      eps(1-m) + m * [1/(M/u + 1/abar)] * (1/u) * S
+ *   GRAD_BLEND PU/...guided_gradient.py:117-118        eps(1-m) + (eps + lam*g) m
+ *   GRAD_ADD   uncertainty_guidance.py:129             eps + lam*g*m
+ *   WEIGHTS    SU/scheduling_ddim_uncertainty_threshold.py:554-574   eps*w; x0 from the UNMASKED eps
+ *   NONE       plain F3
+ * mask source: per-row threshold thr[B] compared with u (strict; `higher`), or an explicit fp32
+ * mask/weight tensor.
+ * ---------------------------------------------------------------------------------------------- */
+enum du_guidance { DU_GUIDE_NONE = 0, DU_GUIDE_POSTERIOR = 1, DU_GUIDE_GRAD_BLEND = 2, DU_GUIDE_GRAD_ADD = 3, DU_GUIDE_WEIGHTS = 4 };
+
+typedef struct du_guided_params {
+  /* inputs */
+  const void* eps;      int64_t eps_stride;    int32_t eps_dtype;    int32_t guidance;
+  const void* sample;   int64_t sample_stride; int32_t sample_dtype; int32_t higher;
+  const float* u;       int64_t u_stride;      /* uncertainty map (POSTERIOR, or thr masks)         */
+  const float* thr;                            /* [B] per-row thresholds, or NULL                   */
+  const float* mask;    int64_t mask_stride;   /* explicit mask / weights, or NULL                  */
+  const void* aux;      int64_t aux_stride;    int32_t aux_dtype;    int32_t aux_broadcast;
+                                               /* POSTERIOR: S (aux_broadcast: one row for all b);
+                                                  GRAD_*: g                                         */
+  float lam;                                   /* lambda_update / lr                                */
+  float post_M;                                /* float(M) of the posterior formula                 */
+  float inv_alpha_hat;                         /* 1 / alpha_hat_t, computed on the host in fp32     */
+  int32_t skip_ddim;                           /* only write eps_out / mask_out                     */
+  du_ddim_coeffs ddim;
+  int64_t B, n;
+  /* outputs, all nullable */
+  void* prev_out;       int64_t prev_stride;   int32_t prev_dtype;   int32_t _pad0;
+  void* x0_out;         int64_t x0_stride;     int32_t x0_dtype;     int32_t _pad1;
+  void* eps_out;        int64_t eps_out_stride; int32_t eps_out_dtype; int32_t _pad2;
+  float* mask_out;      int64_t mask_out_stride;
+} du_guided_params;
+
+int du_guided_step(const du_guided_params* p, du_stream_t stream);
+
+/* F5 helper — S[n] = sum over the batch axis of x (the reference's `pred_epsilon.sum(dim=0)`,
+ * uncertainty_guidance.py:119), accumulated in fp64, deterministic. */
+int du_batch_sum(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, float* out, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F7 — out = a*x + b*noise (one rounding per operation).
+ * SU/scheduling_ddim_uncertainty_zigzag_centered.py:538 (a = sqrt(1-beta_t), b = sqrt(beta_t)),
+ * :593-626 add_noise (a = sqrt(abar_t), b = sqrt(1-abar_t)), uncertainty_guidance.py:87.
+ * ---------------------------------------------------------------------------------------------- */
+int du_perturb(const void* x, int64_t x_stride, int x_dtype, const void* noise, int64_t noise_stride,
+               int noise_dtype, float a, float b, int64_t B, int64_t n, void* out, int64_t out_stride,
+               int out_dtype, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F8 — copy (and convert) one step's map into its slot of the [B, T_uc, ...] accumulation buffer:
+ * dst row b = dst + b*dst_stride.  generate_samples.py:192-201,229-231.
+ * ---------------------------------------------------------------------------------------------- */
+int du_accumulate_slot(const void* src, int64_t src_stride, int src_dtype, int64_t B, int64_t n,
+                       void* dst, int64_t dst_stride, int dst_dtype, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The fused uncertainty step: F1 -> F2a -> F5 -> F3 (+F8) in ONE launch.  One thread-block cluster per
+ * image keeps the image's map (and eps) in distributed shared memory, selects the two order
+ * statistics there, and applies the guided DDIM update, so HBM sees each input and output once
+ * (36 B/element at fp32, M=5).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct du_fused_params {
+  const void* scores[DU_MAX_M]; int32_t M; int32_t score_dtype; int64_t score_stride;
+  const void* eps;      int64_t eps_stride;     /* same dtype as scores                              */
+  const void* sample;   int64_t sample_stride;  int32_t sample_dtype; int32_t moments_mode;
+  const float* S;       int64_t S_stride;       int32_t S_broadcast;  int32_t higher;
+                                                /* posterior sum source (fp32); NULL = eps itself    */
+  float q; int32_t lerp_fma; float post_M; float inv_alpha_hat;
+  du_ddim_coeffs ddim;
+  int64_t B, n;
+  float* unc_out;       int64_t unc_stride;     /* map (or its accumulation slot)                    */
+  float* thr_out;                               /* [B], nullable                                     */
+  void* prev_out;       int64_t prev_stride;    int32_t prev_dtype;   int32_t _pad0;
+  void* x0_out;         int64_t x0_stride;      /* nullable, prev_dtype                              */
+  void* eps_out;        int64_t eps_out_stride; /* nullable, fp32                                    */
+  float* mask_out;      int64_t mask_out_stride;/* nullable                                          */
+} du_fused_params;
+
+/* returns DU_ERR_TOO_LARGE when a row does not fit the cluster's shared memory (use the unfused calls) */
+int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t stream);
+int du_fused_supported(int64_t n, int score_dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DU_B200_H */
