@@ -229,14 +229,15 @@ extern "C" int du_moments(const void* const* scores, int M, int64_t score_stride
                           int64_t B, int64_t n, void* unc_out, int64_t unc_stride, int unc_dtype,
                           float* mean_out, int64_t mean_stride, du_stream_t stream) {
   if (!scores || M < 1 || M > DU_MAX_M) return set_error(DU_ERR_BAD_ARG, "du_moments: M=%d must be in [1,%d]", M, DU_MAX_M);
-  if (B < 0 || n < 0 || !unc_out) return set_error(DU_ERR_BAD_ARG, "du_moments: bad sizes or null output");
+  if (B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_moments: negative size");
+  if (B == 0 || n == 0) return DU_OK;
+  if (!unc_out) return set_error(DU_ERR_BAD_ARG, "du_moments: null output");
   if (mode < DU_MOM_VAR_UNBIASED || mode > DU_MOM_PARTIAL_M2) return set_error(DU_ERR_BAD_ARG, "du_moments: bad mode %d", mode);
   if (!dtype_ok(score_dtype) || !dtype_ok(unc_dtype) || (center && !dtype_ok(center_dtype)))
     return set_error(DU_ERR_DTYPE, "du_moments: unsupported dtype");
   if ((mode == DU_MOM_CENTERED || mode == DU_MOM_VAR_WITH_CENTER) && !center)
     return set_error(DU_ERR_BAD_ARG, "du_moments: mode %d needs a centre tensor", mode);
   if (mode == DU_MOM_VAR_UNBIASED || mode == DU_MOM_RAW || mode == DU_MOM_STD_UNBIASED) center = nullptr;
-  if (B == 0 || n == 0) return DU_OK;
 
   MomentsParams p{};
   const int es = dtype_size(score_dtype);

@@ -133,12 +133,13 @@ extern "C" int du_quantile_threshold(const float* u, int64_t B, int64_t n, int64
                                      float* thr_out, int32_t* rank_out, float* val_out, void* scratch, size_t scratch_bytes,
                                      du_stream_t stream) {
   (void)scratch; (void)scratch_bytes;
-  if (!u || !thr_out || B < 0) return set_error(DU_ERR_BAD_ARG, "du_quantile_threshold: null pointer or negative batch");
+  if (B < 0) return set_error(DU_ERR_BAD_ARG, "du_quantile_threshold: negative batch");
   if (!(q >= 0.0f && q <= 1.0f)) return set_error(DU_ERR_BAD_ARG, "quantile() q values must be in the range [0, 1]");
   if (n <= 0) return set_error(DU_ERR_BAD_ARG, "quantile() input tensor must be non-empty");
   if (n > (int64_t)1 << 24) return set_error(DU_ERR_TOO_LARGE, "quantile() input tensor is too large");
-  if (!aligned(u, 4)) return set_error(DU_ERR_ALIGN, "du_quantile_threshold: misaligned input");
   if (B == 0) return DU_OK;
+  if (!u || !thr_out) return set_error(DU_ERR_BAD_ARG, "du_quantile_threshold: null pointer");
+  if (!aligned(u, 4)) return set_error(DU_ERR_ALIGN, "du_quantile_threshold: misaligned input");
   // torch: ranks = q (fp32 tensor) * (n - 1)  ->  fp32 product; lo = floor, hi = ceil, weight = rank - lo
   volatile float rank = q * (float)(n - 1);
   float fl = floorf(rank), ce = ceilf(rank);

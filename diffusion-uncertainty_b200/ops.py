@@ -58,7 +58,9 @@ class Rows:
         if not batch:
             t = t.reshape(1, -1) if t.is_contiguous() else t.contiguous().reshape(1, -1)
         B = t.shape[0]
-        n = t.numel() // B if B > 0 else 0
+        n = 1
+        for d_ in t.shape[1:]:
+            n *= int(d_)
         # rows must be internally contiguous; the batch stride may be anything (channel-slice views)
         if B > 0 and n > 0 and not t[0].is_contiguous():
             t = t.contiguous()
@@ -112,6 +114,8 @@ def moments(scores: Union[Sequence[torch.Tensor], torch.Tensor], center: Optiona
         raise ValueError("moments: `out` rows must be contiguous")
     _same_rows(r0, orow, "moments(out)")
     mean = torch.empty(shape, device=scores[0].device, dtype=torch.float32) if return_mean else None
+    if out.numel() == 0:
+        return (out, mean) if return_mean else out
     ptrs = (C.c_void_p * len(rows))(*[r.ptr for r in rows])
     rc = L.load().du_moments(ptrs, len(rows), r0.stride, r0.dt,
                              crow.ptr if crow else NULL, crow.stride if crow else 0, crow.dt if crow else 0,
