@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — the uncertainty-step benchmark (BASELINE.json metric: uncertainty-step Mpix/s + % HBM peak).
+
+A "step" is one pass of the hot path over one batch of synthetic score tensors:
+  F1c variance over the M perturbed predictions + eps  ->  F2a per-image percentile threshold + mask
+  ->  F5 posterior score blend  ->  F3 DDIM x_{t-1}  (+F8: the map is written into its accumulation slot)
+Workload (config.workload): ImageNet-128 ADM shapes, batch 128 per GPU, M=5, fp32, q=0.9 — the configuration the
+metric is quoted on (226.5 MB of algorithmic traffic per step, larger than the 126 MB L2).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--dtype fp32|fp16|bf16]
+
+N>1 is launched by torchrun (one rank per GPU); the image batch is sharded by replication of the per-GPU
+batch (weak scaling, no data-path collective: moments are per element, quantiles per image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, C, H, W, M, q)
+    "imagenet128_adm_b128_m5": (128, 3, 128, 128, 5, 0.9),
+    "imagenet64_adm_b128_m5": (128, 3, 64, 64, 5, 0.9),
+    "cifar10_ddpm_b16_m5": (16, 3, 32, 32, 5, 0.95),
+    "uvit256_latent_b128_m5": (128, 4, 32, 32, 5, 0.9),
+    "sd512_latent_b1_m16": (1, 4, 64, 64, 16, 0.9),
+}
+DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
+T_UC = 10            # accumulation slots (num_steps_uc of the README command)
+TIMESTEP = 180       # first uncertainty timestep of `--start-step-uc 40` at 50 steps
+STEP_RATIO = 20
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def algorithmic_bytes_per_element(M, score_bytes, sample_bytes=4):
+    """(M+1)*s_in (scores + eps) + s_x (sample) + 4 (u -> map slot) + s_x (x_{t-1})."""
+    return (M + 1) * score_bytes + sample_bytes + 4 + sample_bytes
+
+
+def ddim_scalars(t=TIMESTEP, ratio=STEP_RATIO):
+    """Scalars of one DDIM step with the reference's fp32 expressions (linear betas 1e-4..0.02,
+    SU/scheduling_ddim_uncertainty_zigzag_centered.py:462-468,507)."""
+    betas = torch.linspace(1e-4, 0.02, 1000, dtype=torch.float32)
+    ac = torch.cumprod(1.0 - betas, dim=0)
+    a_t, a_prev = ac[t], ac[t - ratio] if t - ratio >= 0 else torch.tensor(1.0)
+    return dict(sqrt_alpha_t=(a_t ** 0.5).item(), sqrt_beta_t=((1 - a_t) ** 0.5).item(),
+                sqrt_alpha_prev=(a_prev ** 0.5).item(), dir_coef=((1 - a_prev) ** 0.5).item(), alpha_hat=a_t.item())
+
+
+def synth_host(B, C, H, W, M, dtype, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    eps = torch.randn(B, C, H, W, generator=g)
+    scores = [(eps + 0.05 * torch.randn(B, C, H, W, generator=g)).to(dtype) for _ in range(M)]
+    sample = torch.randn(B, C, H, W, generator=g)
+    eps = eps.to(dtype)
+    if pin:
+        eps, sample, scores = eps.pin_memory(), sample.pin_memory(), [s.pin_memory() for s in scores]
+    return eps, scores, sample
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arms
+def cpu_step_fn(B, C, H, W, M, q):
+    """The reference's torch CPU expressions for the step (oracle/du_oracle.py restates them line for line)."""
+    from oracle import du_oracle as O
+    sc = ddim_scalars()
+    ac = torch.cumprod(1.0 - O.make_betas(), dim=0)
+    c = O.DDIMCoeffs(ac, torch.tensor(1.0), TIMESTEP, TIMESTEP - STEP_RATIO, 0.0)
+    a_hat = ac[TIMESTEP]
+
+    def step(eps, scores, sample):
+        return O.uncertainty_step_posterior(scores, eps, sample, q, M, a_hat, c, clip_sample=True, batch_sum=True)
+    del sc
+    return step
+
+
+def time_cpu(workload, sample_images, budget_s, min_reps=2):
+    B, C, H, W, M, q = WORKLOADS[workload]
+    b = min(B, sample_images)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    eps, scores, sample = synth_host(b, C, H, W, M, torch.float32, 1234, pin=False)
+    step = cpu_step_fn(b, C, H, W, M, q)
+    step(eps, scores, sample)  # warm-up
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        step(eps, scores, sample)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": b * H * W / best / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": f"{b} of {B} images of {workload}, fp32, best of {len(times)} steps ({best * 1e3:.1f} ms/step)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (torch eager expressions, restated in
+    oracle/du_oracle.py and pinned bit-exact to the reference by tests/golden) on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, C, H, W, M, q = WORKLOADS[args.workload]
+    b = min(B, 16)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    eps, scores, sample = synth_host(b, C, H, W, M, torch.float32, 1234, pin=False)
+    step = cpu_step_fn(b, C, H, W, M, q)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step(eps, scores, sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(eps, scores, sample)
+    dt = time.perf_counter() - t0
+    val = b * H * W * args.steps / dt / 1e6
+    line = {"impl": "reference", "metric": "uncertainty_step_throughput", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "batch_per_gpu": B, "M": M, "q": q, "sample_images_per_step": b},
+            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                             "sample": f"{b} of {B} images per step, torch {torch.__version__} CPU, {cores} threads"},
+            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from diffusion_uncertainty_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the uncertainty path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, C, H, W, M, q = WORKLOADS[args.workload]
+    dtype = DTYPES[args.dtype]
+    n_el = B * C * H * W
+    sc = ddim_scalars()
+    coeffs = ops.make_coeffs(sc["sqrt_alpha_t"], sc["sqrt_beta_t"], sc["sqrt_alpha_prev"], sc["dir_coef"], clip_sample=True)
+
+    h_eps, h_scores, h_sample = synth_host(B, C, H, W, M, dtype, 1234 + rank, pin=True)
+    eps, scores, sample = h_eps.to(dev), [s.to(dev) for s in h_scores], h_sample.to(dev)
+    maps = torch.zeros(B, T_UC, C, H, W, device=dev, dtype=torch.float32)   # F8 accumulation buffer
+    S_sum = ops.batch_sum(eps) if args.batch_sum else None
+
+    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step(i, timed=False):
+        slot = maps[:, i % T_UC]
+        if timed:
+            ev_k0[i].record()
+        u = ops.moments(scores, center=eps, mode="var_with_center", out=slot)
+        if timed:
+            ev_k1[i].record()
+        thr = ops.quantile_threshold(u, q)
+        if args.batch_sum:
+            S = ops.batch_sum(eps)
+            r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=S, aux_broadcast=True,
+                                post_M=float(M), inv_alpha_hat=1.0 / sc["alpha_hat"], want_eps=False)
+        else:
+            r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=eps, post_M=float(M),
+                                inv_alpha_hat=1.0 / sc["alpha_hat"], want_eps=False)
+        return r["prev"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            out = step(i, timed=True)
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count - launches0
+    k_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    ms_per_step = ms / args.steps
+    value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    h_prev = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
+    h_map = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(i):
+        d_eps = h_eps.to(dev, non_blocking=True)
+        d_scores = [s.to(dev, non_blocking=True) for s in h_scores]
+        d_sample = h_sample.to(dev, non_blocking=True)
+        r = ops.uncertainty_step(d_scores, d_eps, d_sample, q, coeffs, sc["alpha_hat"], batch_sum=args.batch_sum,
+                                 map_out=maps[:, i % T_UC])
+        h_prev.copy_(r["prev"], non_blocking=True)
+        h_map.copy_(r["u"], non_blocking=True)
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_val = world * B * H * W * e2e_steps / e2e_s / 1e6
+    sb = 4 if dtype == torch.float32 else 2
+    h2d = n_el * ((M + 1) * sb + 4)
+    d2h = n_el * 8
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        alg_step = algorithmic_bytes_per_element(M, sb) * n_el
+        alg_kernel = ((M + 1) * sb + 4) * n_el          # moments kernel: M scores + eps in, u out
+        achieved = alg_kernel / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "uncertainty_step_throughput", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype], "data": "synthetic",
+            "config": {"workload": args.workload, "batch_per_gpu": B, "shape": [C, H, W], "M": M, "q": q,
+                       "chain": "F1c var(M+1) -> F2a quantile mask -> F5 posterior -> F3 DDIM (+F8 slot write)",
+                       "batch_sum": bool(args.batch_sum), "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
+                             if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)},
+            "step_hbm_frac": alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
+            "step_algorithmic_GBps": alg_step / (ms_per_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "moments_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
+                         "kernel_ms": k_ms, "algorithmic_bytes": alg_kernel},
+            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_s / e2e_steps * 1e3},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = time_cpu(args.workload, sample_images=32, budget_s=12.0)
+        print(json.dumps(line), flush=True)
+    del out
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="imagenet128_adm_b128_m5", choices=list(WORKLOADS))
+    ap.add_argument("--dtype", default="fp32", choices=list(DTYPES))
+    ap.add_argument("--batch-sum", type=int, default=1, help="1 = reference behaviour (posterior sum over the batch axis)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -367,3 +367,121 @@ def accumulate_slot(src: torch.Tensor, dst_slot: torch.Tensor):
     _same_rows(s, d, "accumulate_slot")
     L.check(L.load().du_accumulate_slot(s.ptr, s.stride, s.dt, s.B, s.n, d.ptr, d.stride, d.dt, _stream(src)))
     _count()
+
+
+# ------------------------------------------------------------------------------------------------ whole step
+def fused_supported(n: int, dtype: torch.dtype) -> int:
+    """Cluster size the fused kernel would use for rows of n elements (0 = not supported)."""
+    return int(L.load().du_fused_supported(int(n), _DT[dtype]))
+
+
+def fused_uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,
+                           coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
+                           S: Optional[torch.Tensor] = None, S_broadcast: bool = False, higher: bool = True,
+                           map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
+                           want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None):
+    """ONE launch: moments -> per-image quantile -> mask -> posterior blend -> DDIM (du_fused_uncertainty_step)."""
+    M = len(scores)
+    if M < 1 or M > L.DU_MAX_M:
+        raise ValueError(f"fused step: M={M} must be in [1, {L.DU_MAX_M}]")
+    rows = [Rows(t, f"scores[{k}]") for k, t in enumerate(scores)]
+    r0 = rows[0]
+    e, sm = Rows(eps, "eps"), Rows(sample, "sample")
+    for r in rows[1:] + [e]:
+        _same_rows(r0, r, "fused step")
+        if r.dt != r0.dt or r.stride != (r0.stride if r is not e else r.stride):
+            raise RuntimeError("fused step: scores and eps must share dtype (and scores one row stride)")
+    _same_rows(r0, sm, "fused step(sample)")
+    P = L.FusedParams()
+    for k, r in enumerate(rows):
+        P.scores[k] = r.ptr.value
+    P.M, P.score_dtype, P.score_stride = M, r0.dt, r0.stride
+    P.eps, P.eps_stride = e.ptr, e.stride
+    P.sample, P.sample_stride, P.sample_dtype = sm.ptr, sm.stride, sm.dt
+    P.moments_mode = _MODES[moments_mode]
+    keep = [rows, e, sm]
+    if S is not None:
+        if S.dtype != torch.float32:
+            S = S.float()
+        sr = Rows(S, "S", batch=not S_broadcast); keep.append(sr)
+        if sr.n != r0.n:
+            raise ValueError("fused step: S has the wrong number of elements per image")
+        P.S, P.S_stride, P.S_broadcast = sr.ptr, sr.stride, int(S_broadcast)
+    P.higher, P.q, P.lerp_fma = int(higher), float(q), int(bool(lerp_fma))
+    P.post_M = float(M if post_M is None else post_M)
+    P.inv_alpha_hat = float(1.0 / alpha_hat_t)
+    P.ddim = coeffs
+    P.B, P.n = r0.B, r0.n
+    dev, shape = eps.device, eps.shape
+    out_dtype = torch.promote_types(torch.promote_types(eps.dtype, sample.dtype), torch.float32)
+    u = map_out if map_out is not None else torch.empty(shape, device=dev, dtype=torch.float32)
+    ur = Rows(u, "map_out")
+    if ur.t is not u or u.dtype != torch.float32:
+        raise ValueError("fused step: map_out must be a float32 tensor with contiguous rows")
+    _same_rows(r0, ur, "fused step(map_out)")
+    P.unc_out, P.unc_stride = ur.ptr, ur.stride
+    thr = torch.empty(r0.B, device=dev, dtype=torch.float32)
+    P.thr_out = C.c_void_p(thr.data_ptr())
+    res = {"u": u, "thr": thr, "x0": None, "eps": None, "mask": None}
+    res["prev"] = torch.empty(shape, device=dev, dtype=out_dtype)
+    P.prev_out, P.prev_stride, P.prev_dtype = C.c_void_p(res["prev"].data_ptr()), r0.n, _DT[out_dtype]
+    if want_x0:
+        res["x0"] = torch.empty(shape, device=dev, dtype=out_dtype)
+        P.x0_out, P.x0_stride = C.c_void_p(res["x0"].data_ptr()), r0.n
+    if want_eps:
+        res["eps"] = torch.empty(shape, device=dev, dtype=torch.float32)
+        P.eps_out, P.eps_out_stride = C.c_void_p(res["eps"].data_ptr()), r0.n
+    if want_mask:
+        res["mask"] = torch.empty(shape, device=dev, dtype=torch.float32)
+        P.mask_out, P.mask_out_stride = C.c_void_p(res["mask"].data_ptr()), r0.n
+    L.check(L.load().du_fused_uncertainty_step(C.byref(P), _stream(eps)))
+    _count()
+    del keep
+    return res
+
+
+def _fused_eligible(scores, eps, sample, map_out, S) -> bool:
+    n = eps[0].numel() if eps.shape[0] > 0 else 0
+    if n == 0 or eps.dtype not in _DT or not fused_supported(n, eps.dtype):
+        return False
+    vec = 4 if eps.dtype == torch.float32 else 8
+    ts = list(scores) + [eps, sample] + ([map_out] if map_out is not None else []) + ([S] if S is not None else [])
+    for t in ts:
+        if t.data_ptr() % 16 or (t.dim() > 1 and t.shape[0] > 1 and t.stride(0) % vec) or not t[0].is_contiguous():
+            return False
+    return all(s.dtype == eps.dtype for s in scores) and eps.shape[0] <= 65535
+
+
+def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,
+                     coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
+                     sum_source: Optional[torch.Tensor] = None, batch_sum: bool = True, higher: bool = True,
+                     map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
+                     want_eps: bool = False, want_mask: bool = False, fused: Optional[bool] = None):
+    """The percentile-guided posterior step, F1 -> F2a -> F5 -> F3 (+F8 when `map_out` is a slot of the
+    accumulation buffer): PU/...posterior_distribution.py:153-162 + uncertainty_guidance.py:101-120 +
+    SU/...zigzag_centered.py:472-510.  Returns dict(u, thr, prev, x0, eps, mask).
+    batch_sum=True reproduces the reference's `sum(dim=0)` over the batch axis (identity at B=1).
+    fused=None picks the single-launch cluster kernel whenever the shape/alignment allows it."""
+    M = len(scores)
+    for t in list(scores) + [eps, sample]:
+        _require_cuda(t, "uncertainty_step input")
+    src = eps if sum_source is None else sum_source
+    S, bcast = (None if sum_source is None else src), False
+    if batch_sum and eps.shape[0] > 1:
+        S, bcast = batch_sum_fn(src), True
+    if fused is None:
+        fused = _fused_eligible(scores, eps, sample, map_out, S)
+    if fused:
+        return fused_uncertainty_step(scores, eps, sample, q, coeffs, alpha_hat_t, moments_mode=moments_mode, S=S,
+                                      S_broadcast=bcast, higher=higher, map_out=map_out, lerp_fma=lerp_fma, want_x0=want_x0,
+                                      want_eps=want_eps, want_mask=want_mask)
+    u = moments(scores, center=eps, mode=moments_mode, out=map_out)
+    thr = quantile_threshold(u, q, lerp_fma=lerp_fma)
+    r = guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=src if S is None else S, aux_broadcast=bcast,
+                    higher=higher, post_M=float(M), inv_alpha_hat=float(1.0 / alpha_hat_t), want_prev=True, want_x0=want_x0,
+                    want_eps=want_eps, want_mask=want_mask)
+    r["u"], r["thr"] = u, thr
+    return r
+
+
+batch_sum_fn = batch_sum

@@ -1,0 +1,136 @@
+"""The fused single-launch uncertainty step (du_fused_uncertainty_step) against the CPU oracle and against the
+unfused C-ABI chain.  Thresholds / masks must be bit-exact given the same variance tensor; the kernel's own
+variance differs from the oracle's by a few ulp, so mask agreement with the oracle is checked on the elements
+whose variance is not within 1e-5 relative of the threshold."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import du_oracle as O
+from tests.test_ops_gpu import assert_close_rel, bits_equal, coeffs_for, dev, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from diffusion_uncertainty_b200 import ops as _ops
+    return _ops
+
+
+def run_case(ops, B, C, H, M, q, mode, batch_sum, higher, dtype=torch.float32, seed=0, env=None, monkeypatch=None):
+    if env:
+        for k, v in env.items():
+            monkeypatch.setenv(k, str(v))
+    eps, scores, sample = synth(B, C, H, M, seed=seed, spread=0.3 if dtype != torch.float32 else 0.05, dtype=dtype)
+    d = dev()
+    c, k = coeffs_for(ops, 300, 280)
+    a_hat = torch.cumprod(1 - O.make_betas(), 0)[300]
+    n = C * H * H
+    assert ops.fused_supported(n, dtype) > 0
+    sg, eg, xg = [s.to(d) for s in scores], eps.to(d), sample.to(d)
+    S = scores[-1].float().sum(0) if batch_sum else None
+    res = ops.fused_uncertainty_step(sg, eg, xg, q, k, float(a_hat), moments_mode=mode, S=S.to(d) if batch_sum else None,
+                                     S_broadcast=batch_sum, higher=higher, want_x0=True, want_eps=True, want_mask=True)
+    torch.cuda.synchronize()
+    # --- oracle on the same (fp32-upcast) inputs
+    sf, ef = [s.float() for s in scores], eps.float()
+    u_o = {"var_with_center": O.variance_with_center, "centered": O.centered_second_moment}.get(mode, None)
+    u_o = u_o(sf, ef) if u_o else O.variance_unbiased(sf)
+    assert_close_rel(res["u"], u_o, 1e-5, atol=1e-12)
+    # --- exactness GIVEN THE KERNEL'S OWN MAP: threshold, mask, blend, DDIM are bit-identical to the oracle chain on it
+    u_k = res["u"].cpu()
+    kind = "higher" if higher else "lower"
+    thr_o = torch.quantile(u_k.flatten(1), q, dim=1)
+    assert bits_equal(res["thr"], thr_o)
+    mask_o = O.calculate_threshold_map(float(q), None, u_k, kind)
+    assert bits_equal(res["mask"], mask_o)
+    src = ef if not batch_sum else sf[-1]
+    eps_o = O.posterior_blend(ef, u_k, mask_o, M, a_hat, sum_source=src, batch_sum=batch_sum)
+    prev_o, x0_o, _ = O.ddim_step(eps_o, sample, c)
+    assert bits_equal(res["eps"], eps_o) and bits_equal(res["x0"], x0_o) and bits_equal(res["prev"], prev_o)
+    # --- and against the oracle's own variance: masks agree away from the threshold
+    thr2 = torch.quantile(u_o.flatten(1), q, dim=1).view(-1, 1, 1, 1)
+    mask2 = O.calculate_threshold_map(float(q), None, u_o, kind)
+    safe = ((u_o - thr2).abs() > 1e-5 * thr2.abs())
+    assert bits_equal(res["mask"].cpu()[safe], mask2[safe])
+    if mode == "var_with_center":
+        _, mask3, _, prev3, _ = O.uncertainty_step_posterior(sf, ef, sample, q, M, a_hat, c, batch_sum=batch_sum,
+                                                             sum_source=src, threshold_type=kind)
+        assert bits_equal(mask3, mask2)
+        ok = (res["mask"].cpu() == mask3) & torch.isfinite(prev3)
+        assert_close_rel(res["prev"].cpu()[ok], prev3[ok], 1e-4, atol=1e-5)
+    return res
+
+
+@pytest.mark.parametrize("shape", [(4, 3, 32), (3, 4, 16), (2, 3, 64), (130, 3, 16)])
+@pytest.mark.parametrize("mode", ["var_with_center", "centered", "var"])
+def test_fused_matches_oracle(ops, shape, mode):
+    B, C, H = shape
+    run_case(ops, B, C, H, 5, 0.9, mode, batch_sum=False, higher=True, seed=B)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("keep", [0, 1])
+def test_fused_every_cluster_size(ops, monkeypatch, cluster, keep):
+    run_case(ops, 5, 3, 32, 5, 0.95, "var_with_center", batch_sum=True, higher=True, seed=cluster,
+             env={"DU_FUSED_CLUSTER": cluster, "DU_FUSED_KEEP_EPS": keep}, monkeypatch=monkeypatch)
+
+
+@pytest.mark.parametrize("q,higher", [(0.0, True), (1.0, True), (0.5, False), (0.999, True), (0.37, False)])
+def test_fused_quantile_edges(ops, q, higher):
+    run_case(ops, 3, 3, 32, 4, q, "var_with_center", batch_sum=True, higher=higher, seed=7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M", [1, 5, 16])
+def test_fused_16bit_scores(ops, dtype, M):
+    mode = "var_with_center"
+    run_case(ops, 3, 4, 32, M, 0.9, mode, batch_sum=False, higher=True, dtype=dtype, seed=M)
+
+
+def test_fused_ties_and_nan(ops):
+    """quantised scores (massive ties, zero variances) and a NaN image"""
+    d = dev()
+    g = torch.Generator().manual_seed(5)
+    eps = (torch.randn(3, 3, 32, 32, generator=g) * 2).round() / 2
+    scores = [eps + (torch.randn(3, 3, 32, 32, generator=g)).round() * 0.5 for _ in range(4)]
+    scores[1][2, 0, 0, 0] = float("nan")
+    sample = torch.randn(3, 3, 32, 32, generator=g)
+    c, k = coeffs_for(ops, 300, 280)
+    a_hat = torch.cumprod(1 - O.make_betas(), 0)[300]
+    res = ops.fused_uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), 0.9, k, float(a_hat), want_mask=True,
+                                     want_eps=True)
+    u_k = res["u"].cpu()
+    thr_o = torch.quantile(u_k.flatten(1), 0.9, dim=1)
+    assert bits_equal(res["thr"], thr_o) and torch.isnan(thr_o[2])
+    mask_o = O.calculate_threshold_map(0.9, None, u_k, "higher")
+    assert bits_equal(res["mask"], mask_o) and mask_o[2].sum() == 0
+    eps_o = O.posterior_blend(eps, u_k, mask_o, 4, a_hat, batch_sum=False)
+    assert bits_equal(res["eps"], eps_o)
+
+
+def test_fused_equals_unfused_chain_and_slot_write(ops):
+    d = dev()
+    eps, scores, sample = synth(6, 3, 32, 5, seed=3)
+    c, k = coeffs_for(ops, 180, 160)
+    a_hat = float(torch.cumprod(1 - O.make_betas(), 0)[180])
+    sg, eg, xg = [s.to(d) for s in scores], eps.to(d), sample.to(d)
+    buf = torch.zeros(6, 4, 3, 32, 32, device=d)
+    a = ops.uncertainty_step(sg, eg, xg, 0.9, k, a_hat, batch_sum=True, map_out=buf[:, 2], fused=True, want_mask=True)
+    b = ops.uncertainty_step(sg, eg, xg, 0.9, k, a_hat, batch_sum=True, fused=False, want_mask=True)
+    assert bits_equal(buf[:, 2], b["u"]) and bits_equal(a["thr"], b["thr"]) and bits_equal(a["mask"], b["mask"])
+    assert bits_equal(a["prev"], b["prev"])
+    assert float(buf[:, 1].abs().max()) == 0.0 and float(buf[:, 3].abs().max()) == 0.0
+
+
+def test_fused_unsupported_falls_back_to_unfused_kernels(ops):
+    """rows too long for cluster shared memory (or ragged) are served by the unfused CUDA chain — never by a CPU path"""
+    d = dev()
+    n_big = 3 * 512 * 512
+    assert ops.fused_supported(n_big, torch.float32) == 0
+    eps, scores, sample = synth(2, 1, 15, 3, seed=1)   # 225 elements per image: not a multiple of 4
+    c, k = coeffs_for(ops, 180, 160)
+    r = ops.uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), 0.9, k, 0.5, batch_sum=False, want_mask=True)
+    u2, mask2, _, prev2, _ = O.uncertainty_step_posterior(scores, eps, sample, 0.9, 3, torch.tensor(0.5), c, batch_sum=False)
+    assert_close_rel(r["u"], u2, 1e-5)
