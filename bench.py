@@ -200,26 +200,39 @@ def run_ours(args):
     h_eps, h_scores, h_sample = synth_host(B, C, H, W, M, dtype, 1234 + rank, pin=True)
     eps, scores, sample = h_eps.to(dev), [s.to(dev) for s in h_scores], h_sample.to(dev)
     maps = torch.zeros(B, T_UC, C, H, W, device=dev, dtype=torch.float32)   # F8 accumulation buffer
-    S_sum = ops.batch_sum(eps) if args.batch_sum else None
 
     ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    S_buf = torch.empty(C, H, W, device=dev, dtype=torch.float32)
+    fused = (not args.unfused) and ops.fused_supported(C * H * W, dtype) > 0
+    plan = None
+    if fused:
+        # the prepared single-launch step (ops.FusedStep == du_fused_uncertainty_step): F1c -> F2a -> F5 -> F3 (+F8)
+        plan = ops.FusedStep(scores, eps, sample, q, coeffs, sc["alpha_hat"], S=S_buf if args.batch_sum else None,
+                             S_broadcast=bool(args.batch_sum), map_out=maps[:, 0])
+    dominant = "fused_step_kernel" if fused else "moments_kernel"
 
     def step(i, timed=False):
         slot = maps[:, i % T_UC]
+        if args.batch_sum:
+            ops.batch_sum(eps, out=S_buf)            # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
+        if fused:
+            plan.set_map_out(slot)
+            if timed:
+                ev_k0[i].record()
+            r = plan.launch()
+            if timed:
+                ev_k1[i].record()
+            return r["prev"]
         if timed:
             ev_k0[i].record()
         u = ops.moments(scores, center=eps, mode="var_with_center", out=slot)
         if timed:
             ev_k1[i].record()
         thr = ops.quantile_threshold(u, q)
-        if args.batch_sum:
-            S = ops.batch_sum(eps)
-            r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=S, aux_broadcast=True,
-                                post_M=float(M), inv_alpha_hat=1.0 / sc["alpha_hat"], want_eps=False)
-        else:
-            r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=eps, post_M=float(M),
-                                inv_alpha_hat=1.0 / sc["alpha_hat"], want_eps=False)
+        r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=S_buf if args.batch_sum else eps,
+                            aux_broadcast=bool(args.batch_sum), post_M=float(M), inv_alpha_hat=1.0 / sc["alpha_hat"],
+                            want_eps=False)
         return r["prev"]
 
     def barrier():
@@ -242,6 +255,17 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = ops.launch_count - launches0
     k_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps
+    k_bb_ms = None
+    if fused:   # cross-check of the per-launch figure: the same kernel launched back to back, two events around all K
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        b0.record()
+        for i in range(args.steps):
+            plan.set_map_out(maps[:, i % T_UC])
+            plan.launch()
+        b1.record()
+        torch.cuda.synchronize()
+        k_bb_ms = b0.elapsed_time(b1) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -282,7 +306,8 @@ def run_ours(args):
     if rank == 0:
         peak, peak_kind = peaks()
         alg_step = algorithmic_bytes_per_element(M, sb) * n_el
-        alg_kernel = ((M + 1) * sb + 4) * n_el          # moments kernel: M scores + eps in, u out
+        # dominant kernel: the fused step moves exactly the step's algorithmic bytes; unfused: moments = M scores + eps in, u out
+        alg_kernel = alg_step if fused else ((M + 1) * sb + 4) * n_el
         achieved = alg_kernel / (k_ms * 1e-3) / 1e9
         line = {
             "metric": "uncertainty_step_throughput", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -290,14 +315,14 @@ def run_ours(args):
             "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype], "data": "synthetic",
             "config": {"workload": args.workload, "batch_per_gpu": B, "shape": [C, H, W], "M": M, "q": q,
                        "chain": "F1c var(M+1) -> F2a quantile mask -> F5 posterior -> F3 DDIM (+F8 slot write)",
-                       "batch_sum": bool(args.batch_sum), "parallelism": f"batch-sharded x{world}, no collective",
+                       "batch_sum": bool(args.batch_sum), "fused_single_launch": bool(fused), "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
                              if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)},
             "step_hbm_frac": alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
             "step_algorithmic_GBps": alg_step / (ms_per_step * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "moments_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
-                         "kernel_ms": k_ms, "algorithmic_bytes": alg_kernel},
+                         "kernel_ms": k_ms, "kernel_ms_back_to_back": k_bb_ms, "algorithmic_bytes": alg_kernel},
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / e2e_steps * 1e3},
             "gpu_launches": launches,
@@ -321,6 +346,7 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=list(DTYPES))
     ap.add_argument("--batch-sum", type=int, default=1, help="1 = reference behaviour (posterior sum over the batch axis)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--unfused", action="store_true", help="time the 3-kernel chain instead of the single fused launch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -337,10 +337,13 @@ def guided_step(eps: torch.Tensor, sample: Optional[torch.Tensor], coeffs: Optio
     return res
 
 
-def batch_sum(x: torch.Tensor) -> torch.Tensor:
+def batch_sum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x.sum(dim=0) as fp32 (du_batch_sum) — the reference's batch-axis sum of the posterior score."""
     r = Rows(x, "x")
-    out = torch.empty(x.shape[1:], device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(x.shape[1:], device=x.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != r.n or not out.is_cuda:
+        raise ValueError("batch_sum: `out` must be a contiguous float32 CUDA tensor of one image's size")
     L.check(L.load().du_batch_sum(r.ptr, r.stride, r.dt, r.B, r.n, C.c_void_p(out.data_ptr()), _stream(x)))
     _count()
     return out
@@ -375,69 +378,95 @@ def fused_supported(n: int, dtype: torch.dtype) -> int:
     return int(L.load().du_fused_supported(int(n), _DT[dtype]))
 
 
+class FusedStep:
+    """A prepared du_fused_uncertainty_step call: the parameter block is built once, `launch()` is a single
+    C-ABI call (one kernel launch), so a sampling loop (or a CUDA-graph capture) pays no per-step Python
+    marshalling.  Outputs live in `self.res` (dict u, thr, prev, x0, eps, mask) and are overwritten by every
+    launch; `set_map_out()` re-targets the map at another slot of the accumulation buffer (F8)."""
+
+    def __init__(self, scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,
+                 coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
+                 S: Optional[torch.Tensor] = None, S_broadcast: bool = False, higher: bool = True,
+                 map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
+                 want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None):
+        M = len(scores)
+        if M < 1 or M > L.DU_MAX_M:
+            raise ValueError(f"fused step: M={M} must be in [1, {L.DU_MAX_M}]")
+        rows = [Rows(t, f"scores[{k}]") for k, t in enumerate(scores)]
+        r0 = rows[0]
+        e, sm = Rows(eps, "eps"), Rows(sample, "sample")
+        for r in rows[1:] + [e]:
+            _same_rows(r0, r, "fused step")
+            if r.dt != r0.dt or r.stride != (r0.stride if r is not e else r.stride):
+                raise RuntimeError("fused step: scores and eps must share dtype (and scores one row stride)")
+        _same_rows(r0, sm, "fused step(sample)")
+        P = L.FusedParams()
+        for k, r in enumerate(rows):
+            P.scores[k] = r.ptr.value
+        P.M, P.score_dtype, P.score_stride = M, r0.dt, r0.stride
+        P.eps, P.eps_stride = e.ptr, e.stride
+        P.sample, P.sample_stride, P.sample_dtype = sm.ptr, sm.stride, sm.dt
+        P.moments_mode = _MODES[moments_mode]
+        self._keep = [rows, e, sm]
+        if S is not None:
+            if S.dtype != torch.float32:
+                S = S.float()
+            sr = Rows(S, "S", batch=not S_broadcast)
+            self._keep.append(sr)
+            if sr.n != r0.n:
+                raise ValueError("fused step: S has the wrong number of elements per image")
+            P.S, P.S_stride, P.S_broadcast = sr.ptr, sr.stride, int(S_broadcast)
+        P.higher, P.q, P.lerp_fma = int(higher), float(q), int(bool(lerp_fma))
+        P.post_M = float(M if post_M is None else post_M)
+        P.inv_alpha_hat = float(1.0 / alpha_hat_t)
+        P.ddim = coeffs
+        P.B, P.n = r0.B, r0.n
+        dev, shape = eps.device, eps.shape
+        out_dtype = torch.promote_types(torch.promote_types(eps.dtype, sample.dtype), torch.float32)
+        self.P, self._r0, self._dev_tensor = P, r0, eps
+        thr = torch.empty(r0.B, device=dev, dtype=torch.float32)
+        P.thr_out = C.c_void_p(thr.data_ptr())
+        res = {"u": None, "thr": thr, "x0": None, "eps": None, "mask": None}
+        res["prev"] = torch.empty(shape, device=dev, dtype=out_dtype)
+        P.prev_out, P.prev_stride, P.prev_dtype = C.c_void_p(res["prev"].data_ptr()), r0.n, _DT[out_dtype]
+        if want_x0:
+            res["x0"] = torch.empty(shape, device=dev, dtype=out_dtype)
+            P.x0_out, P.x0_stride = C.c_void_p(res["x0"].data_ptr()), r0.n
+        if want_eps:
+            res["eps"] = torch.empty(shape, device=dev, dtype=torch.float32)
+            P.eps_out, P.eps_out_stride = C.c_void_p(res["eps"].data_ptr()), r0.n
+        if want_mask:
+            res["mask"] = torch.empty(shape, device=dev, dtype=torch.float32)
+            P.mask_out, P.mask_out_stride = C.c_void_p(res["mask"].data_ptr()), r0.n
+        self.res = res
+        self.set_map_out(map_out if map_out is not None else torch.empty(shape, device=dev, dtype=torch.float32))
+        self._fn = L.load().du_fused_uncertainty_step
+        self._ref = C.byref(P)
+
+    def set_map_out(self, u: torch.Tensor):
+        ur = Rows(u, "map_out")
+        if ur.t is not u or u.dtype != torch.float32:
+            raise ValueError("fused step: map_out must be a float32 tensor with contiguous rows")
+        _same_rows(self._r0, ur, "fused step(map_out)")
+        self.P.unc_out, self.P.unc_stride = ur.ptr, ur.stride
+        self.res["u"] = u
+
+    def set_S(self, S: torch.Tensor, broadcast: bool):
+        sr = Rows(S, "S", batch=not broadcast)
+        self._keep.append(sr)
+        self.P.S, self.P.S_stride, self.P.S_broadcast = sr.ptr, sr.stride, int(broadcast)
+
+    def launch(self):
+        L.check(self._fn(self._ref, _stream(self._dev_tensor)))
+        _count()
+        return self.res
+
+
 def fused_uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,
-                           coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
-                           S: Optional[torch.Tensor] = None, S_broadcast: bool = False, higher: bool = True,
-                           map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
-                           want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None):
-    """ONE launch: moments -> per-image quantile -> mask -> posterior blend -> DDIM (du_fused_uncertainty_step)."""
-    M = len(scores)
-    if M < 1 or M > L.DU_MAX_M:
-        raise ValueError(f"fused step: M={M} must be in [1, {L.DU_MAX_M}]")
-    rows = [Rows(t, f"scores[{k}]") for k, t in enumerate(scores)]
-    r0 = rows[0]
-    e, sm = Rows(eps, "eps"), Rows(sample, "sample")
-    for r in rows[1:] + [e]:
-        _same_rows(r0, r, "fused step")
-        if r.dt != r0.dt or r.stride != (r0.stride if r is not e else r.stride):
-            raise RuntimeError("fused step: scores and eps must share dtype (and scores one row stride)")
-    _same_rows(r0, sm, "fused step(sample)")
-    P = L.FusedParams()
-    for k, r in enumerate(rows):
-        P.scores[k] = r.ptr.value
-    P.M, P.score_dtype, P.score_stride = M, r0.dt, r0.stride
-    P.eps, P.eps_stride = e.ptr, e.stride
-    P.sample, P.sample_stride, P.sample_dtype = sm.ptr, sm.stride, sm.dt
-    P.moments_mode = _MODES[moments_mode]
-    keep = [rows, e, sm]
-    if S is not None:
-        if S.dtype != torch.float32:
-            S = S.float()
-        sr = Rows(S, "S", batch=not S_broadcast); keep.append(sr)
-        if sr.n != r0.n:
-            raise ValueError("fused step: S has the wrong number of elements per image")
-        P.S, P.S_stride, P.S_broadcast = sr.ptr, sr.stride, int(S_broadcast)
-    P.higher, P.q, P.lerp_fma = int(higher), float(q), int(bool(lerp_fma))
-    P.post_M = float(M if post_M is None else post_M)
-    P.inv_alpha_hat = float(1.0 / alpha_hat_t)
-    P.ddim = coeffs
-    P.B, P.n = r0.B, r0.n
-    dev, shape = eps.device, eps.shape
-    out_dtype = torch.promote_types(torch.promote_types(eps.dtype, sample.dtype), torch.float32)
-    u = map_out if map_out is not None else torch.empty(shape, device=dev, dtype=torch.float32)
-    ur = Rows(u, "map_out")
-    if ur.t is not u or u.dtype != torch.float32:
-        raise ValueError("fused step: map_out must be a float32 tensor with contiguous rows")
-    _same_rows(r0, ur, "fused step(map_out)")
-    P.unc_out, P.unc_stride = ur.ptr, ur.stride
-    thr = torch.empty(r0.B, device=dev, dtype=torch.float32)
-    P.thr_out = C.c_void_p(thr.data_ptr())
-    res = {"u": u, "thr": thr, "x0": None, "eps": None, "mask": None}
-    res["prev"] = torch.empty(shape, device=dev, dtype=out_dtype)
-    P.prev_out, P.prev_stride, P.prev_dtype = C.c_void_p(res["prev"].data_ptr()), r0.n, _DT[out_dtype]
-    if want_x0:
-        res["x0"] = torch.empty(shape, device=dev, dtype=out_dtype)
-        P.x0_out, P.x0_stride = C.c_void_p(res["x0"].data_ptr()), r0.n
-    if want_eps:
-        res["eps"] = torch.empty(shape, device=dev, dtype=torch.float32)
-        P.eps_out, P.eps_out_stride = C.c_void_p(res["eps"].data_ptr()), r0.n
-    if want_mask:
-        res["mask"] = torch.empty(shape, device=dev, dtype=torch.float32)
-        P.mask_out, P.mask_out_stride = C.c_void_p(res["mask"].data_ptr()), r0.n
-    L.check(L.load().du_fused_uncertainty_step(C.byref(P), _stream(eps)))
-    _count()
-    del keep
-    return res
+                           coeffs: L.DdimCoeffs, alpha_hat_t: float, **kw):
+    """ONE launch: moments -> per-image quantile -> mask -> posterior blend -> DDIM (du_fused_uncertainty_step).
+    Keyword arguments as FusedStep."""
+    return FusedStep(scores, eps, sample, q, coeffs, alpha_hat_t, **kw).launch()
 
 
 def _fused_eligible(scores, eps, sample, map_out, S) -> bool:

@@ -361,3 +361,17 @@ def test_accumulate_slot(ops):
     bufh = torch.empty(3, 4, 2, 8, 8, device=d, dtype=torch.float16)
     ops.accumulate_slot(maps[1].to(d), bufh[:, 1])
     assert bits_equal(bufh[:, 1], maps[1].half())
+
+
+@pytest.mark.parametrize("B,n_shape,dtype", [(128, (3, 32, 32), torch.float32), (37, (4, 16, 16), torch.float32),
+                                             (5, (3, 8, 8), torch.float32), (19, (1, 15, 15), torch.float32),
+                                             (64, (4, 32, 32), torch.float16)])
+def test_batch_sum(ops, B, n_shape, dtype):
+    """du_batch_sum (cluster/DSMEM path for B >= 16 and vectorisable rows, scalar path otherwise) == x.sum(0) in fp64"""
+    g = torch.Generator().manual_seed(B)
+    x = torch.randn(B, *n_shape, generator=g).to(dtype)
+    got = ops.batch_sum(x.to(dev()))
+    want = x.double().sum(0).float()
+    assert bits_equal(got, want)
+    out = torch.empty(n_shape, device=dev())
+    assert ops.batch_sum(x.to(dev()), out=out) is out and bits_equal(out, want)
