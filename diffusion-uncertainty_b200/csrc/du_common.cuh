@@ -39,17 +39,109 @@ __device__ __forceinline__ void store1(void* base, int64_t idx, int dt, float v)
   else reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
 }
 
-// streaming 128-bit load: read-only path, do not allocate in L1
+// streaming 128-bit load: read-only path, do not allocate in L1.  volatile so that the compiler never
+// speculates a predicated load (a null score pointer past M would fault); callers therefore issue a whole batch
+// of these in program order BEFORE the first use (memory-level parallelism is what the reduction kernels live on).
 __device__ __forceinline__ uint4 ldg_stream_128(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 __device__ __forceinline__ uint2 ldg_stream_64(const void* p) {
   uint2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
   return r;
+}
+
+// 16-byte vector of T (4 fp32 or 8 fp16/bf16): raw load now, unpack to fp32 at the point of use
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int VEC = 4;
+  static constexpr int DT = DU_F32;
+  __device__ static __forceinline__ uint4 load(const void* base, int64_t idx) {
+    return ldg_stream_128(reinterpret_cast<const float*>(base) + idx);
+  }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int VEC = 8;
+  static constexpr int DT = DU_F16;
+  __device__ static __forceinline__ uint4 load(const void* base, int64_t idx) {
+    return ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
+  }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __half2float(__ushort_as_half((unsigned short)(w[i] & 0xffff)));
+      v[2 * i + 1] = __half2float(__ushort_as_half((unsigned short)(w[i] >> 16)));
+    }
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  static constexpr int DT = DU_BF16;
+  __device__ static __forceinline__ uint4 load(const void* base, int64_t idx) {
+    return ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
+  }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[8]) {
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+};
+
+// Shifted-data accumulation of one batch of score vectors (SURVEY.md §7 "Variance numerics"): d = x - k with
+// k the first sample (variance modes) or the centre; s1 = sum d, s2 = sum d^2.
+constexpr int DU_LOAD_BATCH = 8;  // score vectors in flight per thread (16 B each)
+
+// centre_mode: 0 = no centre, 1 = centre is the shift k (DU_MOM_CENTERED), 2 = centre is one more sample
+// (DU_MOM_VAR_WITH_CENTER).  raw_c is the already-issued 16-byte load of the centre vector; it is unpacked only
+// after the first batch of score loads has been issued, so all of them are in flight together (c_ready: the caller
+// already filled c[], e.g. from a centre tensor of another dtype).
+template <typename T>
+__device__ __forceinline__ void accumulate_scores(const void* const* scores, int M, int64_t off, const uint4& raw_c,
+                                                  int centre_mode, bool c_ready, bool shift_first, float (&c)[Vec16<T>::VEC],
+                                                  float (&k)[Vec16<T>::VEC], float (&s1)[Vec16<T>::VEC],
+                                                  float (&s2)[Vec16<T>::VEC]) {
+  using V = Vec16<T>;
+  constexpr int VEC = V::VEC;
+  for (int m0 = 0; m0 < M; m0 += DU_LOAD_BATCH) {
+    uint4 raw[DU_LOAD_BATCH];
+#pragma unroll
+    for (int j = 0; j < DU_LOAD_BATCH; ++j)
+      if (m0 + j < M) raw[j] = V::load(scores[m0 + j], off);
+    if (m0 == 0) {
+      if (centre_mode && !c_ready) V::unpack(raw_c, c);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) { k[e] = (centre_mode == 1) ? c[e] : 0.0f; s1[e] = 0.0f; s2[e] = 0.0f; }
+    }
+#pragma unroll
+    for (int j = 0; j < DU_LOAD_BATCH; ++j) {
+      if (m0 + j < M) {
+        float x[VEC];
+        V::unpack(raw[j], x);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          if (shift_first && m0 + j == 0) k[e] = x[e];
+          const float d = x[e] - k[e];
+          s1[e] += d;
+          s2[e] = fmaf(d, d, s2[e]);
+        }
+      }
+    }
+  }
+  if (centre_mode == 2) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float d = c[e] - k[e];
+      s1[e] += d;
+      s2[e] = fmaf(d, d, s2[e]);
+    }
+  }
 }
 
 // 4 consecutive elements starting at element index idx (idx % 4 == 0, pointer suitably aligned)

@@ -28,33 +28,6 @@ struct FusedKParams {
   float w;          // lerp weight
 };
 
-template <typename T> struct FVec;
-template <> struct FVec<float> {
-  static constexpr int VEC = 4;
-  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[4]) {
-    uint4 r = ldg_stream_128(reinterpret_cast<const float*>(base) + idx);
-    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
-  }
-};
-template <> struct FVec<__half> {
-  static constexpr int VEC = 8;
-  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[8]) {
-    uint4 r = ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
-    uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = f16_bits_to_float(w[i] & 0xffff); v[2 * i + 1] = f16_bits_to_float(w[i] >> 16); }
-  }
-};
-template <> struct FVec<__nv_bfloat16> {
-  static constexpr int VEC = 8;
-  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[8]) {
-    uint4 r = ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
-    uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = bf16_bits_to_float(w[i] & 0xffff); v[2 * i + 1] = bf16_bits_to_float(w[i] >> 16); }
-  }
-};
-
 // warp 0 locates rank k in a 256-bin histogram (generic pointer: may be DSMEM); result -> res[0..2]
 __device__ __forceinline__ void locate_bin_256(const uint32_t* hist, uint32_t k, uint32_t* res) {
   const int lane = threadIdx.x;
@@ -78,9 +51,9 @@ __device__ __forceinline__ void locate_bin_256(const uint32_t* hist, uint32_t k,
   }
 }
 
-template <typename T, bool KEEP_EPS>
-__global__ void __launch_bounds__(512) fused_step_kernel(const __grid_constant__ FusedKParams kp) {
-  using FV = FVec<T>;
+template <typename T, bool KEEP_EPS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) fused_step_kernel(const __grid_constant__ FusedKParams kp) {
+  using FV = Vec16<T>;
   constexpr int VEC = FV::VEC;
   const du_fused_params& p = kp.p;
   cg::cluster_group cluster = cg::this_cluster();
@@ -114,48 +87,17 @@ __global__ void __launch_bounds__(512) fused_step_kernel(const __grid_constant__
   const int count = p.M + (extra ? 1 : 0);
   const float cnt = (float)count;
   uint32_t nan_seen = 0;
+  const int centre_mode = centered ? 1 : (extra ? 2 : 0);
   for (int64_t g = tid; g < L / VEC; g += T_) {
     const int64_t i = base + g * VEC;
     float c[VEC], k[VEC], s1[VEC], s2[VEC];
-    FV::load(p.eps, b * p.eps_stride + i, c);
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) { k[e] = centered ? c[e] : 0.0f; s1[e] = 0.0f; s2[e] = 0.0f; }
-    const int64_t off = b * p.score_stride + i;
-    int m = 0;
-    for (; m + 4 <= p.M; m += 4) {
-      float x[4][VEC];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) FV::load(p.scores[m + j], off, x[j]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          if (!centered && m + j == 0) k[e] = x[j][e];
-          float d = x[j][e] - k[e];
-          s1[e] += d;
-          s2[e] = fmaf(d, d, s2[e]);
-        }
-      }
-    }
-    for (; m < p.M; ++m) {
-      float x[VEC];
-      FV::load(p.scores[m], off, x);
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        if (!centered && m == 0) k[e] = x[e];
-        float d = x[e] - k[e];
-        s1[e] += d;
-        s2[e] = fmaf(d, d, s2[e]);
-      }
-    }
+    uint4 raw_c = make_uint4(0u, 0u, 0u, 0u);
+    if (KEEP_EPS || centre_mode) raw_c = FV::load(p.eps, b * p.eps_stride + i);
+    accumulate_scores<T>(p.scores, p.M, b * p.score_stride + i, raw_c, centre_mode, false, !centered, c, k, s1, s2);
+    if (KEEP_EPS && centre_mode == 0) FV::unpack(raw_c, c);
     float u[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (extra) {
-        float d = c[e] - k[e];
-        s1[e] += d;
-        s2[e] = fmaf(d, d, s2[e]);
-      }
       if (centered) {
         u[e] = s2[e] / cnt;
       } else {
@@ -239,41 +181,54 @@ __global__ void __launch_bounds__(512) fused_step_kernel(const __grid_constant__
   du_ddim_coeffs dc = p.ddim;
   dc.add_noise = 0;
   const bool higher = p.higher != 0;
-  for (int64_t g = tid; g < L / 4; g += T_) {
-    const int64_t i = base + 4 * g;
-    float4 u4 = *reinterpret_cast<const float4*>(u_s + 4 * g);
-    float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-    float e0[4], s[4], S[4];
-    if (KEEP_EPS) {
-      float4 e4 = *reinterpret_cast<const float4*>(eps_s + 4 * g);
-      e0[0] = e4.x; e0[1] = e4.y; e0[2] = e4.z; e0[3] = e4.w;
-    } else {
-      load4(p.eps, b * p.eps_stride + i, p.score_dtype, e0);
-    }
-    load4(p.sample, b * p.sample_stride + i, p.sample_dtype, s);
-    if (p.S) {
-      float4 s4 = __ldg(reinterpret_cast<const float4*>(p.S + (p.S_broadcast ? 0 : b * p.S_stride) + i));
-      S[0] = s4.x; S[1] = s4.y; S[2] = s4.z; S[3] = s4.w;
-    } else {
+  constexpr int UNR = 2;  // groups per thread per trip: all global loads of a trip are issued before the arithmetic
+  for (int64_t g0 = tid; g0 < L / 4; g0 += (int64_t)UNR * T_) {
+    float s[UNR][4], S[UNR][4], e0[UNR][4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) S[e] = e0[e];
+    for (int r = 0; r < UNR; ++r) {
+      const int64_t g = g0 + (int64_t)r * T_;
+      if (g < L / 4) {
+        const int64_t i = base + 4 * g;
+        load4(p.sample, b * p.sample_stride + i, p.sample_dtype, s[r]);
+        if (!KEEP_EPS) load4(p.eps, b * p.eps_stride + i, p.score_dtype, e0[r]);
+        if (p.S) {
+          float4 s4 = __ldg(reinterpret_cast<const float4*>(p.S + (p.S_broadcast ? 0 : b * p.S_stride) + i));
+          S[r][0] = s4.x; S[r][1] = s4.y; S[r][2] = s4.z; S[r][3] = s4.w;
+        }
+      }
     }
-    float pv[4], x0v[4], eg[4], mk[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      mk[e] = (higher ? (uu[e] > thr) : (uu[e] < thr)) ? 1.0f : 0.0f;
-      float inv_var = __fdiv_rn(1.0f, uu[e]);
-      float trace = __fadd_rn(__fmul_rn(p.post_M, inv_var), p.inv_alpha_hat);
-      float prec = __fdiv_rn(1.0f, trace);
-      float post = __fmul_rn(prec, __fmul_rn(inv_var, S[e]));
-      eg[e] = __fadd_rn(__fmul_rn(e0[e], __fsub_rn(1.0f, mk[e])), __fmul_rn(mk[e], post));
-      DdimOut o = ddim_update(eg[e], s[e], 0.0f, dc);
-      pv[e] = o.prev; x0v[e] = o.x0;
+    for (int r = 0; r < UNR; ++r) {
+      const int64_t g = g0 + (int64_t)r * T_;
+      if (g >= L / 4) break;
+      const int64_t i = base + 4 * g;
+      float4 u4 = *reinterpret_cast<const float4*>(u_s + 4 * g);
+      float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+      if (KEEP_EPS) {
+        float4 e4 = *reinterpret_cast<const float4*>(eps_s + 4 * g);
+        e0[r][0] = e4.x; e0[r][1] = e4.y; e0[r][2] = e4.z; e0[r][3] = e4.w;
+      }
+      if (!p.S) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) S[r][e] = e0[r][e];
+      }
+      float pv[4], x0v[4], eg[4], mk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mk[e] = (higher ? (uu[e] > thr) : (uu[e] < thr)) ? 1.0f : 0.0f;
+        float inv_var = __fdiv_rn(1.0f, uu[e]);
+        float trace = __fadd_rn(__fmul_rn(p.post_M, inv_var), p.inv_alpha_hat);
+        float prec = __fdiv_rn(1.0f, trace);
+        float post = __fmul_rn(prec, __fmul_rn(inv_var, S[r][e]));
+        eg[e] = __fadd_rn(__fmul_rn(e0[r][e], __fsub_rn(1.0f, mk[e])), __fmul_rn(mk[e], post));
+        DdimOut o = ddim_update(eg[e], s[r][e], 0.0f, dc);
+        pv[e] = o.prev; x0v[e] = o.x0;
+      }
+      store4(p.prev_out, b * p.prev_stride + i, p.prev_dtype, pv);
+      if (p.x0_out) store4(p.x0_out, b * p.x0_stride + i, p.prev_dtype, x0v);
+      if (p.eps_out) store4(p.eps_out, b * p.eps_out_stride + i, DU_F32, eg);
+      if (p.mask_out) store4(p.mask_out, b * p.mask_out_stride + i, DU_F32, mk);
     }
-    store4(p.prev_out, b * p.prev_stride + i, p.prev_dtype, pv);
-    if (p.x0_out) store4(p.x0_out, b * p.x0_stride + i, p.prev_dtype, x0v);
-    if (p.eps_out) store4(p.eps_out, b * p.eps_out_stride + i, DU_F32, eg);
-    if (p.mask_out) store4(p.mask_out, b * p.mask_out_stride + i, DU_F32, mk);
   }
   if (csize > 1) cluster.sync();  // keep CTA 0's shared memory alive until every peer has read it
 }
@@ -305,17 +260,15 @@ static bool fused_plan(int64_t n, int vec, FusedPlan* out) {
   if (!best_c) return false;
   int64_t L = n / best_c;
   int64_t groups = L / vec;
-  int threads = 512;
-  while (threads > 64 && groups < threads) threads >>= 1;
-  if (threads < 256) threads = 256;  // the histogram merge uses threads 0..255
-  if (e_t) threads = atoi(e_t);
+  int threads = (groups >= 1024) ? 512 : 256;  // the histogram merge uses threads 0..255
+  if (e_t) threads = (atoi(e_t) == 512) ? 512 : 256;
   out->cluster = best_c; out->keep_eps = best_keep; out->threads = threads; out->smem = fused_smem_bytes(L, best_keep);
   return true;
 }
 
-template <typename T, bool KEEP>
-static int launch_fused(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
-  auto kern = fused_step_kernel<T, KEEP>;
+template <typename T, bool KEEP, int THREADS>
+static int launch_fused_t(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
+  auto kern = fused_step_kernel<T, KEEP, THREADS>;
   DU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)plan.cluster, (unsigned)kp.p.B, 1);
@@ -331,6 +284,12 @@ static int launch_fused(const FusedKParams& kp, const FusedPlan& plan, cudaStrea
   cfg.numAttrs = 1;
   DU_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
   return DU_OK;
+}
+
+template <typename T, bool KEEP>
+static int launch_fused(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
+  if (plan.threads == 512) return launch_fused_t<T, KEEP, 512>(kp, plan, st);
+  return launch_fused_t<T, KEEP, 256>(kp, plan, st);
 }
 
 }  // namespace du

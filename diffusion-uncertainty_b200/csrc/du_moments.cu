@@ -26,36 +26,6 @@ struct MomentsParams {
   int64_t mean_stride;
 };
 
-template <typename T> struct ScoreVec;
-template <> struct ScoreVec<float> {
-  static constexpr int VEC = 4;
-  static constexpr int DT = DU_F32;
-  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[4]) {
-    uint4 r = ldg_stream_128(reinterpret_cast<const float*>(base) + idx);
-    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
-  }
-};
-template <> struct ScoreVec<__half> {
-  static constexpr int VEC = 8;
-  static constexpr int DT = DU_F16;
-  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[8]) {
-    uint4 r = ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
-    uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = f16_bits_to_float(w[i] & 0xffff); v[2 * i + 1] = f16_bits_to_float(w[i] >> 16); }
-  }
-};
-template <> struct ScoreVec<__nv_bfloat16> {
-  static constexpr int VEC = 8;
-  static constexpr int DT = DU_BF16;
-  __device__ static __forceinline__ void load(const void* base, int64_t idx, float (&v)[8]) {
-    uint4 r = ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
-    uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = bf16_bits_to_float(w[i] & 0xffff); v[2 * i + 1] = bf16_bits_to_float(w[i] >> 16); }
-  }
-};
-
 // Accumulator for one element.
 struct Acc {
   float k;   // shift (first sample) for variance modes, centre for DU_MOM_CENTERED, 0 for RAW
@@ -79,76 +49,51 @@ __device__ __forceinline__ float finish(const Acc& a, int mode, bool centered, i
 // VECTOR = false is the scalar fallback for unaligned / ragged views.
 template <typename T, bool VECTOR>
 __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ MomentsParams p) {
-  using SV = ScoreVec<T>;
+  using SV = Vec16<T>;
   constexpr int VEC = VECTOR ? SV::VEC : 1;
   const int64_t groups = (p.n + VEC - 1) / VEC;
   const int mode = p.mode;
   const bool centered = (mode == DU_MOM_CENTERED) || (mode == DU_MOM_PARTIAL_M2 && p.center != nullptr);
   const bool shifted = !(centered || mode == DU_MOM_RAW);
   const bool extra = (mode == DU_MOM_VAR_WITH_CENTER);
+  const int count = p.M + (extra ? 1 : 0);
 
   for (int64_t b = blockIdx.y; b < p.B; b += gridDim.y) {
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
       const int64_t i = g * VEC;
       Acc acc[VEC];
-      float c[VEC];
-      if (p.center != nullptr) {
-        if constexpr (VECTOR) {
-          if (p.center_dtype == SV::DT) {
-            SV::load(p.center, b * p.center_stride + i, c);
-          } else {
+      if constexpr (VECTOR) {
+        // every 16-byte load of this group (centre + up to DU_LOAD_BATCH scores) is issued before the first use
+        float c[VEC], k[VEC], s1[VEC], s2[VEC];
+        const bool same_dt = (p.center != nullptr) && (p.center_dtype == SV::DT);
+        uint4 raw_c = make_uint4(0u, 0u, 0u, 0u);
+        if (same_dt) raw_c = SV::load(p.center, b * p.center_stride + i);
+        const int centre_mode = (p.center == nullptr) ? 0 : (centered ? 1 : (extra ? 2 : 0));
+        if (centre_mode && !same_dt) {  // mixed dtypes (e.g. fp32 eps with fp16 scores): scalar loads of the centre
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) c[e] = load1(p.center, b * p.center_stride + i + e, p.center_dtype);
-          }
-        } else {
-          c[0] = load1(p.center, b * p.center_stride + i, p.center_dtype);
+          for (int e = 0; e < VEC; ++e) c[e] = load1(p.center, b * p.center_stride + i + e, p.center_dtype);
+        }
+        accumulate_scores<T>(p.scores, p.M, b * p.score_stride + i, raw_c, centre_mode, !same_dt, shifted, c, k, s1, s2);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { acc[e].k = k[e]; acc[e].s1 = s1[e]; acc[e].s2 = s2[e]; }
+      } else {
+        float c0 = 0.0f;
+        if (p.center != nullptr) c0 = load1(p.center, b * p.center_stride + i, p.center_dtype);
+        acc[0].k = centered ? c0 : 0.0f; acc[0].s1 = 0.0f; acc[0].s2 = 0.0f;
+        const int64_t off = b * p.score_stride + i;
+        for (int m = 0; m < p.M; ++m) {
+          const float x = load1(p.scores[m], off, SV::DT);
+          if (shifted && m == 0) acc[0].k = x;
+          const float d = x - acc[0].k;
+          acc[0].s1 += d;
+          acc[0].s2 = fmaf(d, d, acc[0].s2);
+        }
+        if (extra) {
+          const float d = c0 - acc[0].k;
+          acc[0].s1 += d;
+          acc[0].s2 = fmaf(d, d, acc[0].s2);
         }
       }
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) { acc[e].k = centered ? c[e] : 0.0f; acc[e].s1 = 0.0f; acc[e].s2 = 0.0f; }
-
-      const int64_t off = b * p.score_stride + i;
-      int m = 0;
-      // chunks of 4 tensors: issue all loads of the chunk before consuming them (MLP)
-      for (; m + 4 <= p.M; m += 4) {
-        float x[4][VEC];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if constexpr (VECTOR) SV::load(p.scores[m + j], off, x[j]);
-          else x[j][0] = load1(p.scores[m + j], off, SV::DT);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            if (shifted && m + j == 0) acc[e].k = x[j][e];
-            float d = x[j][e] - acc[e].k;
-            acc[e].s1 += d;
-            acc[e].s2 = fmaf(d, d, acc[e].s2);
-          }
-        }
-      }
-      for (; m < p.M; ++m) {
-        float x[VEC];
-        if constexpr (VECTOR) SV::load(p.scores[m], off, x);
-        else x[0] = load1(p.scores[m], off, SV::DT);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          if (shifted && m == 0) acc[e].k = x[e];
-          float d = x[e] - acc[e].k;
-          acc[e].s1 += d;
-          acc[e].s2 = fmaf(d, d, acc[e].s2);
-        }
-      }
-      if (extra) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          float d = c[e] - acc[e].k;
-          acc[e].s1 += d;
-          acc[e].s2 = fmaf(d, d, acc[e].s2);
-        }
-      }
-      const int count = p.M + (extra ? 1 : 0);
       float u[VEC], mu[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) u[e] = finish(acc[e], mode, centered, count, p.mean ? &mu[e] : nullptr);
@@ -173,7 +118,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ Mo
 
 template <typename T>
 static int launch_moments(const MomentsParams& p, bool vec, cudaStream_t st) {
-  constexpr int VEC = ScoreVec<T>::VEC;
+  constexpr int VEC = Vec16<T>::VEC;
   const int threads = 256;
   int64_t groups = vec ? (p.n / VEC) : p.n;
   RowGrid g = row_grid(p.B, groups, threads);
