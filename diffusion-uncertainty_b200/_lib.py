@@ -94,6 +94,7 @@ PROTOTYPES = {
     "du_batch_sum": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, vp]),
     "du_perturb": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, f32, f32, i64, i64, vp, i64, C.c_int, vp]),
     "du_accumulate_slot": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, C.c_int, vp]),
+    "du_image_uint8": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, vp]),
     "du_fused_uncertainty_step": (C.c_int, [C.POINTER(FusedParams), vp]),
     "du_fused_supported": (C.c_int, [i64, C.c_int]),
 }

@@ -55,6 +55,11 @@ __device__ __forceinline__ uint2 ldg_stream_64(const void* p) {
 }
 
 // 16-byte vector of T (4 fp32 or 8 fp16/bf16): raw load now, unpack to fp32 at the point of use
+// uniform row pointer + 32-bit per-thread byte offset: two integer instructions per load instead of a 64-bit multiply-add
+__device__ __forceinline__ uint4 ldg_stream_128_at(const void* row, uint32_t byte_off) {
+  return ldg_stream_128(reinterpret_cast<const char*>(row) + byte_off);
+}
+
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int VEC = 4;
@@ -142,6 +147,60 @@ __device__ __forceinline__ void accumulate_scores(const void* const* scores, int
       s2[e] = fmaf(d, d, s2[e]);
     }
   }
+}
+
+// Same contract as accumulate_scores with M known at compile time: no predication, every load of a batch (<= 8 score
+// vectors + the centre) is issued before the first use.
+template <typename T, int MT>
+__device__ __forceinline__ void accumulate_scores_ct(const void* const* scores, int64_t row_off, uint32_t byte_off, const uint4& raw_c,
+                                                     int centre_mode, bool c_ready, bool shift_first,
+                                                     float (&c)[Vec16<T>::VEC], float (&k)[Vec16<T>::VEC],
+                                                     float (&s1)[Vec16<T>::VEC], float (&s2)[Vec16<T>::VEC]) {
+  using V = Vec16<T>;
+  constexpr int VEC = V::VEC;
+  constexpr int BATCH = (MT <= 8) ? MT : 8;
+  uint4 raw[BATCH];
+#pragma unroll
+  for (int m = 0; m < BATCH; ++m) raw[m] = ldg_stream_128_at(reinterpret_cast<const T*>(scores[m]) + row_off, byte_off);
+  if (centre_mode && !c_ready) V::unpack(raw_c, c);
+  if (centre_mode == 1) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) k[e] = c[e];
+  } else if (shift_first) {
+    V::unpack(raw[0], k);
+  } else {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) k[e] = 0.0f;
+  }
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) { s1[e] = 0.0f; s2[e] = 0.0f; }
+#pragma unroll
+  for (int m0 = 0; m0 < MT; m0 += BATCH) {
+    if (m0 > 0) {
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j)
+        if (m0 + j < MT) raw[j] = ldg_stream_128_at(reinterpret_cast<const T*>(scores[m0 + j]) + row_off, byte_off);
+    }
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) {
+      if (m0 + j < MT) {
+        float x[VEC];
+        V::unpack(raw[j], x);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { const float d = x[e] - k[e]; s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+      }
+    }
+  }
+  if (centre_mode == 2) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { const float d = c[e] - k[e]; s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+  }
+}
+
+// sum of squared deviations about the mean from the shifted sums (NaN is kept; tiny negative rounding residue -> 0)
+__device__ __forceinline__ float m2_from_sums(float s1, float s2, float inv_cnt) {
+  const float m2 = fmaf(-s1 * inv_cnt, s1, s2);
+  return (m2 < 0.0f) ? 0.0f : m2;
 }
 
 // 4 consecutive elements starting at element index idx (idx % 4 == 0, pointer suitably aligned)

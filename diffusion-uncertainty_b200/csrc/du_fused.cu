@@ -1,17 +1,30 @@
 // du_fused.cu — the fused uncertainty step: F1 (moments over M) -> F2a (per-image quantile + mask) -> F5
 // (posterior score) -> F3 (DDIM x_{t-1}) (+F8: the map goes straight to its accumulation slot), ONE launch.
 //
-// One thread-block CLUSTER per image.  Each CTA of the cluster owns a contiguous slice of the image:
-//   phase A  streams the M score tensors + eps of its slice through registers (128-bit L1-bypassing loads,
-//            every HBM byte read once), writes the map to global memory AND keeps it (and eps) in shared
-//            memory, and histograms the top key byte on the fly;
-//   phase B  MSB-first radix select (4 x 8 bit) of the lo-th / hi-th order statistic over the
-//            DISTRIBUTED shared-memory copy of the map: per-CTA histograms are merged into CTA 0's shared
-//            memory with DSMEM atomics, two cluster barriers per level, no global-memory traffic at all;
-//   phase C  threshold = torch's lerp of the two statistics; mask, posterior blend and DDIM update on the
-//            slice, reading u/eps from shared memory and only `sample` from HBM; x_{t-1} written once.
-// HBM traffic = (M+1)*s_in + 4 (map) + s_x (sample) + s_x (x_{t-1}) bytes per element: the algorithmic minimum.
+// One thread-block CLUSTER per image, every cluster of the batch resident at once (one wave).  Each CTA owns a
+// contiguous slice of its image:
+//   phase A  streams the M score tensors (+ eps) of the slice through registers (128-bit L1-bypassing loads, M is a
+//            template parameter so all M+1 loads of a group are in flight together), writes the map to its
+//            accumulation slot AND keeps it in shared memory, and histograms the top 11 value bits on the fly.
+//            The map is a variance / second moment, i.e. >= +0, so its IEEE bit pattern IS its order-preserving key.
+//   phase B  exact radix select (11 + 10 + 10 bits) of the lo-th / hi-th order statistic over the DISTRIBUTED
+//            shared-memory copy of the map: each CTA histograms its slice locally, one cluster barrier per level,
+//            every CTA then sums the peers' histograms through DSMEM and locates the rank itself — no global-memory
+//            traffic.  While the select runs, the slice of `sample` and `eps` that phase C needs is pulled into L2
+//            with cp.async.bulk.prefetch, so HBM stays busy.
+//   phase C  threshold = torch's lerp of the two statistics; mask, posterior blend and DDIM update on the slice,
+//            u from shared memory, sample/eps from L2; x_{t-1} written once.
+// HBM traffic = (M+1)*s_in + 4 (map) + s_x (sample) + s_x (x_{t-1}) bytes per element: the algorithmic minimum
+// (eps is read twice, the second time from L2).
+//
+// Arithmetic: fp32.  Thresholds and masks are exact functions of the map (bit-identical to torch.quantile /
+// compare on the same map).  The blend and the DDIM update use reciprocal-multiply instead of IEEE division
+// (<= 2 ulp per operation, far inside the 1e-5 relative bar of BASELINE.json); the unfused kernels in du_step.cu keep
+// one IEEE rounding per reference operation.
 #include <cooperative_groups.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include "du_common.cuh"
 
@@ -19,260 +32,510 @@ namespace cg = cooperative_groups;
 
 namespace du {
 
-constexpr int FUSED_LEVELS = 4;  // 4 x 8-bit digits
+constexpr int H0_BITS = 11, H1_BITS = 10, H2_BITS = 10;  // 31 value bits (sign is always 0)
+constexpr int H0_BINS = 1 << H0_BITS, H1_BINS = 1 << H1_BITS, H2_BINS = 1 << H2_BITS;
+constexpr int CAND_CAP = H1_BINS + H2_BINS;  // candidate list (keys of the selected level-0 bin) overlays the level-1/2 histograms
+constexpr int HIST_WORDS = H0_BINS + H1_BINS + H2_BINS;
+// misc words: [0..2] locate result, [3] nan flag, [4] min larger key, [5] next bin, [6] candidate count, [7] threshold,
+// [8..39] warp sums, [40] "successor not among the candidates" flag, [41] key_lo
+constexpr int MISC_WORDS = 48;
+constexpr int MAX_CLUSTER = 8;
 
 struct FusedKParams {
   du_fused_params p;
   int64_t L;        // elements per CTA slice (n / cluster size)
   uint32_t lo, hi;  // ranks
   float w;          // lerp weight
+  float inv_cnt, inv_cm1, inv_sqrt_alpha_t;
+  unsigned long long* timeline;  // debug (DU_FUSED_TIMELINE): [CTA][8] globaltimer stamps at the phase boundaries, else null
 };
 
-// warp 0 locates rank k in a 256-bin histogram (generic pointer: may be DSMEM); result -> res[0..2]
-__device__ __forceinline__ void locate_bin_256(const uint32_t* hist, uint32_t k, uint32_t* res) {
-  const int lane = threadIdx.x;
-  uint32_t c[8], tot = 0;
+__device__ __forceinline__ void stamp(const FusedKParams& kp, int slot) {
+  if (kp.timeline && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    kp.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
+}
+
+// ---- phase A: the map value of one group of VEC elements --------------------------------------------------------------
+// centre_mode: 0 variance over the M scores, 1 second moment about the centre, 2 variance over scores + centre.
+// MT > 0: M known at compile time (all loads of the group in flight together); MT == 0: batched runtime-M loop.
+template <typename T, int MT>
+__device__ __forceinline__ void moments_group(const du_fused_params& p, int64_t srow, int64_t erow, uint32_t g_elems, int centre_mode,
+                                              float inv_cnt, float inv_cm1, float (&u)[Vec16<T>::VEC]) {
+  using V = Vec16<T>;
+  constexpr int VEC = V::VEC;
+  float c[VEC], k[VEC], s1[VEC], s2[VEC];
+  uint4 raw_c = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t byte_off = g_elems * (uint32_t)sizeof(T);
+  if (centre_mode) raw_c = ldg_stream_128_at(reinterpret_cast<const T*>(p.eps) + erow, byte_off);
+  if constexpr (MT > 0) accumulate_scores_ct<T, MT>(p.scores, srow, byte_off, raw_c, centre_mode, false, centre_mode != 1, c, k, s1, s2);
+  else accumulate_scores<T>(p.scores, p.M, srow + g_elems, raw_c, centre_mode, false, centre_mode != 1, c, k, s1, s2);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { c[j] = hist[8 * lane + j]; tot += c[j]; }
+  for (int e = 0; e < VEC; ++e) {
+    // + 0.0f: never -0.0, so the bit pattern of the map orders like its value
+    u[e] = (centre_mode == 1) ? fmaf(s2[e], inv_cnt, 0.0f) : fmaf(m2_from_sums(s1[e], s2[e], inv_cnt), inv_cm1, 0.0f);
+  }
+}
+
+// ---- phase B: block-wide search of rank k in the histogram summed over the cluster's CTAs ----------------------------
+// hist_local points at this CTA's histogram for the level; peers are reached through DSMEM.  Result in misc[0..2]
+// (bin, count below the bin, count in the bin); for LAST also misc[5] = next non-empty bin above (or NBINS).
+template <int NBINS, int THREADS, bool LAST>
+__device__ __forceinline__ void locate_rank(cg::cluster_group& cluster, unsigned csize, uint32_t* hist_local, uint32_t k,
+                                            uint32_t* misc) {
+  constexpr int PER = (NBINS + THREADS - 1) / THREADS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t c[PER], tot = 0;
+  const int first = tid * PER;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) c[j] = 0;
+  if (first < NBINS) {
+    for (unsigned r = 0; r < csize; ++r) {
+      const uint32_t* h = (csize > 1) ? cluster.map_shared_rank(hist_local, r) : hist_local;
+      if constexpr (PER % 4 == 0) {   // one 16-byte (DSMEM) load per 4 bins
+#pragma unroll
+        for (int j = 0; j < PER; j += 4) {
+          const uint4 q = *reinterpret_cast<const uint4*>(h + first + j);
+          c[j] += q.x; c[j + 1] += q.y; c[j + 2] += q.z; c[j + 3] += q.w;
+        }
+      } else if constexpr (PER % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < PER; j += 2) {
+          const uint2 q = *reinterpret_cast<const uint2*>(h + first + j);
+          c[j] += q.x; c[j + 1] += q.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) c[j] += h[first + j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j) tot += c[j];
   uint32_t incl = tot;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += v;
   }
-  uint32_t excl = incl - tot;
-  if (k >= excl && k < incl) {
+  uint32_t* wsum = misc + 8;
+  if (lane == 31) wsum[warp] = incl;
+  if (LAST && tid == 0) misc[5] = NBINS;
+  __syncthreads();
+  uint32_t wprefix = 0;
+  for (int wI = 0; wI < warp; ++wI) wprefix += wsum[wI];
+  const uint32_t excl = wprefix + incl - tot;
+  if (k >= excl && k < excl + tot) {
     uint32_t cum = excl;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (k < cum + c[j]) { res[0] = 8 * lane + j; res[1] = cum; res[2] = c[j]; break; }
+    for (int j = 0; j < PER; ++j) {
+      if (k < cum + c[j]) { misc[0] = first + j; misc[1] = cum; misc[2] = c[j]; break; }
       cum += c[j];
     }
   }
+  __syncthreads();
+  if (LAST) {
+    const uint32_t sel = misc[0];
+    uint32_t nb = NBINS;
+#pragma unroll
+    for (int j = PER - 1; j >= 0; --j)
+      if (c[j] != 0 && (uint32_t)(first + j) > sel) nb = first + j;
+    nb = __reduce_min_sync(0xffffffffu, nb);
+    if (lane == 0 && nb < (uint32_t)NBINS) atomicMin(&misc[5], nb);
+    __syncthreads();
+  }
 }
 
-template <typename T, bool KEEP_EPS, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) fused_step_kernel(const __grid_constant__ FusedKParams kp) {
+__device__ __forceinline__ float rcp_fast(float x) {  // MUFU.RCP: <= 1 ulp, rcp(0) = inf, rcp(inf) = 0
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float clamp_nan(float x, float lo, float hi) {  // torch.clamp: NaN in -> NaN out
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(hi));
+  return r;
+}
+// hist[bin]++ iff a == b, as ONE predicated instruction (the compiler turns `if (..) atomicAdd` into a divergent branch
+// per element, which made the select passes issue-bound)
+__device__ __forceinline__ void hist_inc_if_eq(uint32_t hist_smem_addr, uint32_t bin, uint32_t a, uint32_t b) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, %3;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+               ::"r"(hist_smem_addr + bin * 4u), "r"(1u), "r"(a), "r"(b) : "memory");
+}
+
+// cluster-wide barrier with release/acquire on shared::cluster (what the DSMEM histogram exchange needs)
+// Only shared-memory histograms cross CTAs here.  They are complete in the owning SM's shared memory once the CTA
+// barrier in front has been passed, so the cluster barrier itself is relaxed: the release form costs a MEMBAR.ALL.GPU
+// (it waits for every outstanding global store of phase A).
+__device__ __forceinline__ void cluster_barrier() {
+  __syncthreads();
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---- phase B: the per-image threshold ------------------------------------------------------------------------------------
+// Level 0 (top 11 value bits) was histogrammed on the fly in phase A.  Fast path: the elements of the selected level-0
+// bin (typically ~2 % of the image) are compacted into a candidate list in ONE pass over the shared-memory map, CTA 0
+// gathers the cluster's lists through DSMEM and finishes the exact select on the list alone (two 10-bit levels, a few
+// elements per thread), then publishes the threshold to its peers.  Heavy ties (more than CAND_CAP elements in the bin)
+// take the general path: two more full histogram passes with one cluster barrier each.
+template <int THREADS>
+__device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, unsigned csize, unsigned crank, const FusedKParams& kp,
+                                                  const float* u_s, uint32_t* h0, uint32_t* work, uint32_t* misc) {
+  const int tid = threadIdx.x;
+  const int ng4 = (int)(kp.L / 4);
+  constexpr int LOW = H1_BITS + H2_BITS;
+  auto sync_all = [&]() { if (csize > 1) cluster_barrier(); else __syncthreads(); };
+  auto peer = [&](uint32_t* ptr, unsigned r) -> uint32_t* { return (csize > 1) ? cluster.map_shared_rank(ptr, r) : ptr; };
+
+  sync_all();  // level-0 histograms of every CTA are complete
+  stamp(kp, 2);
+  locate_rank<H0_BINS, THREADS, false>(cluster, csize, h0, kp.lo, misc);
+  const uint32_t d0 = misc[0], below0 = misc[1], cnt0 = misc[2];
+  __syncthreads();
+  stamp(kp, 3);
+  const uint32_t want = d0 << LOW, msk0 = (uint32_t)(H0_BINS - 1) << LOW;
+  float thr;
+
+  if (cnt0 <= (uint32_t)CAND_CAP) {
+    // ---- compaction, warp-aggregated: one shared-memory atomic per warp and trip (a single list cursor hit by every
+    // matching lane serialises), lanes place their keys behind the warp's reservation by an intra-warp prefix count
+    const int lane = tid & 31;
+    const int trips = (ng4 + THREADS - 1) / THREADS;
+#pragma unroll 2
+    for (int it = 0; it < trips; ++it) {
+      const int g = it * THREADS + tid;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      bool m0 = false, m1 = false, m2 = false, m3 = false;
+      if (g < ng4) {
+        v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
+        m0 = (v.x & msk0) == want; m1 = (v.y & msk0) == want; m2 = (v.z & msk0) == want; m3 = (v.w & msk0) == want;
+      }
+      const uint32_t mine = (uint32_t)m0 + (uint32_t)m1 + (uint32_t)m2 + (uint32_t)m3;
+      if (__any_sync(0xffffffffu, mine != 0)) {
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        uint32_t base_slot = 0;
+        if (lane == 31) base_slot = atomicAdd(&misc[6], incl);
+        base_slot = __shfl_sync(0xffffffffu, base_slot, 31);
+        uint32_t slot = base_slot + incl - mine;
+        if (m0) work[slot++] = v.x & 0x7fffffffu;
+        if (m1) work[slot++] = v.y & 0x7fffffffu;
+        if (m2) work[slot++] = v.z & 0x7fffffffu;
+        if (m3) work[slot++] = v.w & 0x7fffffffu;
+      }
+    }
+    sync_all();  // candidate lists complete
+    stamp(kp, 4);
+    if (crank == 0) {
+      uint32_t total = misc[6];
+      bool has_nan = misc[3] != 0;
+      for (unsigned r = 1; r < csize; ++r) {  // gather the peers' candidates behind the local ones
+        const uint32_t* pm = peer(misc, r);
+        const uint32_t* pw = peer(work, r);
+        const uint32_t cr = pm[6];
+        has_nan |= (pm[3] != 0);
+        for (uint32_t j = tid; j < cr; j += THREADS) work[total + j] = pw[j];
+        total += cr;
+      }
+      for (int j = tid; j < H0_BINS; j += THREADS) h0[j] = 0;  // reused: [0,1024) level 1, [1024,2048) level 2
+      __syncthreads();
+      for (uint32_t j = tid; j < total; j += THREADS) atomicAdd(&h0[(work[j] >> H2_BITS) & (H1_BINS - 1)], 1u);
+      __syncthreads();
+      locate_rank<H1_BINS, THREADS, false>(cluster, 1u, h0, kp.lo - below0, misc);
+      const uint32_t d1 = misc[0], below1 = misc[1];
+      __syncthreads();
+      const uint32_t prefix21 = want | (d1 << H2_BITS);
+      for (uint32_t j = tid; j < total; j += THREADS) {
+        const uint32_t key = work[j];
+        if ((key & ~(uint32_t)(H2_BINS - 1)) == prefix21) atomicAdd(&h0[H1_BINS + (key & (H2_BINS - 1))], 1u);
+      }
+      __syncthreads();
+      locate_rank<H2_BINS, THREADS, false>(cluster, 1u, h0 + H1_BINS, kp.lo - below0 - below1, misc);
+      const uint32_t key_lo = prefix21 | misc[0];
+      const uint32_t below = below0 + below1 + misc[1], bincount = misc[2];
+      __syncthreads();
+      const bool need_next = kp.hi >= below + bincount;  // the hi-th statistic is the smallest key above key_lo
+      if (need_next) {
+        uint32_t best = 0xffffffffu;
+        for (uint32_t j = tid; j < total; j += THREADS) { const uint32_t key = work[j]; if (key > key_lo && key < best) best = key; }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
+        __syncthreads();
+      }
+      if (tid == 0) {
+        const uint32_t key_hi = need_next ? misc[4] : key_lo;
+        const bool rare = need_next && key_hi == 0xffffffffu && !has_nan;  // key_lo is the largest key of its level-0 bin
+        float t = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, kp.p.lerp_fma);
+        if (has_nan) t = __int_as_float(0x7fc00000);
+        for (unsigned r = 0; r < csize; ++r) {
+          uint32_t* pm = peer(misc, r);
+          pm[7] = __float_as_uint(t); pm[40] = rare ? 1u : 0u; pm[41] = key_lo;
+        }
+      }
+    }
+    sync_all();  // threshold published
+    thr = __uint_as_float(misc[7]);
+    if (misc[40]) {  // rare: the successor of key_lo lives in a higher level-0 bin -> one pass for the smallest key above
+      const uint32_t key_lo = misc[41];
+      if (tid == 0) misc[4] = 0xffffffffu;
+      __syncthreads();
+      uint32_t best = 0xffffffffu;
+      for (int g = tid; g < ng4; g += THREADS) {
+        const uint4 v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
+        const uint32_t kk[4] = {v.x & 0x7fffffffu, v.y & 0x7fffffffu, v.z & 0x7fffffffu, v.w & 0x7fffffffu};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) best = min(best, (kk[e] > key_lo) ? kk[e] : 0xffffffffu);
+      }
+      best = __reduce_min_sync(0xffffffffu, best);
+      if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
+      sync_all();
+      uint32_t key_hi = 0xffffffffu;
+      for (unsigned r = 0; r < csize; ++r) key_hi = min(key_hi, peer(misc, r)[4]);
+      thr = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, kp.p.lerp_fma);
+    }
+  } else {
+    // ---- general path: two more histogram levels over the whole slice
+    uint32_t* h1 = work;
+    uint32_t* h2 = work + H1_BINS;
+    uint32_t k_rank = kp.lo - below0, below = below0;
+    {
+      const uint32_t h1a = (uint32_t)__cvta_generic_to_shared(h1);
+#pragma unroll 4
+      for (int g = tid; g < ng4; g += THREADS) {
+        const uint4 v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
+        hist_inc_if_eq(h1a, (v.x >> H2_BITS) & (H1_BINS - 1), v.x & msk0, want);
+        hist_inc_if_eq(h1a, (v.y >> H2_BITS) & (H1_BINS - 1), v.y & msk0, want);
+        hist_inc_if_eq(h1a, (v.z >> H2_BITS) & (H1_BINS - 1), v.z & msk0, want);
+        hist_inc_if_eq(h1a, (v.w >> H2_BITS) & (H1_BINS - 1), v.w & msk0, want);
+      }
+    }
+    sync_all();
+    locate_rank<H1_BINS, THREADS, false>(cluster, csize, h1, k_rank, misc);
+    const uint32_t d1 = misc[0];
+    k_rank -= misc[1];
+    below += misc[1];
+    __syncthreads();
+    const uint32_t prefix21 = want | (d1 << H2_BITS);
+    {
+      const uint32_t msk = 0x7fffffffu & ~(uint32_t)(H2_BINS - 1), top = prefix21 | (H2_BINS - 1);
+      const uint32_t h2a = (uint32_t)__cvta_generic_to_shared(h2);
+      uint32_t best = 0xffffffffu;
+#pragma unroll 4
+      for (int g = tid; g < ng4; g += THREADS) {
+        const uint4 v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
+        const uint32_t kk[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t key = kk[e] & 0x7fffffffu;
+          hist_inc_if_eq(h2a, key & (H2_BINS - 1), key & msk, prefix21);
+          best = min(best, (key > top) ? key : 0xffffffffu);
+        }
+      }
+      best = __reduce_min_sync(0xffffffffu, best);
+      if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
+    }
+    sync_all();
+    locate_rank<H2_BINS, THREADS, true>(cluster, csize, h2, k_rank, misc);
+    const uint32_t key_lo = prefix21 | misc[0];
+    below += misc[1];
+    const uint32_t bincount = misc[2];
+    uint32_t key_hi = key_lo;
+    if (kp.hi >= below + bincount) {
+      if (misc[5] < (uint32_t)H2_BINS) {
+        key_hi = prefix21 | misc[5];
+      } else {
+        uint32_t best = 0xffffffffu;
+        for (unsigned r = 0; r < csize; ++r) best = min(best, peer(misc, r)[4]);
+        key_hi = best;
+      }
+    }
+    bool has_nan = false;
+    for (unsigned r = 0; r < csize; ++r) has_nan |= (peer(misc, r)[3] != 0);
+    thr = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, kp.p.lerp_fma);
+    if (has_nan) thr = __int_as_float(0x7fc00000);
+  }
+  if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // last DSMEM access is behind us
+  return thr;
+}
+
+
+// ---- phase C: threshold mask + posterior blend + DDIM update of one slice -----------------------------------------------
+// FAST: epsilon prediction, fp32 sample and outputs (every BASELINE configuration); the generic instantiation covers
+// the other prediction types and 16-bit samples.
+template <typename T, int THREADS, bool FAST>
+__device__ __forceinline__ void guided_update_slice(const FusedKParams& kp, const float* u_s, float thr, int64_t b, int64_t base) {
+  using FV = Vec16<T>;
+  const du_fused_params& p = kp.p;
+  const du_ddim_coeffs dc = p.ddim;
+  const bool higher = p.higher != 0;
+  const float post_M = p.post_M, inv_ah = p.inv_alpha_hat, inv_sa = kp.inv_sqrt_alpha_t;
+  const float inv_sb = FAST ? 0.0f : 1.0f / dc.sqrt_beta_t;
+  const int tid = threadIdx.x;
+  const int ng4 = (int)(kp.L / 4);
+  const int64_t xrow = b * p.sample_stride + base, erow = b * p.eps_stride + base;
+  const float* Srow = p.S ? (p.S + (p.S_broadcast ? 0 : b * p.S_stride) + base) : nullptr;
+  const int pt = FAST ? DU_PRED_EPSILON : dc.prediction_type;
+  const bool reclip = FAST ? false : (dc.use_clipped_model_output != 0);
+#pragma unroll 4
+  for (int g = tid; g < ng4; g += THREADS) {
+    float s[4], e0[4], S[4];
+    if (FAST) {
+      const uint4 r = ldg_stream_128(reinterpret_cast<const float*>(p.sample) + xrow + 4 * g);
+      s[0] = __uint_as_float(r.x); s[1] = __uint_as_float(r.y); s[2] = __uint_as_float(r.z); s[3] = __uint_as_float(r.w);
+    } else {
+      load4(p.sample, xrow + 4 * g, p.sample_dtype, s);
+    }
+    load4(p.eps, erow + 4 * g, FV::DT, e0);
+    if (Srow) {
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(Srow + 4 * g));
+      S[0] = s4.x; S[1] = s4.y; S[2] = s4.z; S[3] = s4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) S[e] = e0[e];
+    }
+    const float4 u4 = *reinterpret_cast<const float4*>(u_s + 4 * g);
+    const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+    float pv[4], x0v[4], eg[4], mk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      mk[e] = (higher ? (uu[e] > thr) : (uu[e] < thr)) ? 1.0f : 0.0f;
+      const float inv_var = rcp_fast(uu[e]);                        // 1/u (u = 0 -> inf, as the reference)
+      const float prec = rcp_fast(fmaf(post_M, inv_var, inv_ah));   // 1/(M/u + 1/abar)
+      const float post = prec * (inv_var * S[e]);
+      eg[e] = fmaf(mk[e], post, e0[e] * (1.0f - mk[e]));            // eps(1-m) + m*post (NaN/inf of `post` propagate)
+      float x0, en;
+      if (pt == DU_PRED_EPSILON) { x0 = (s[e] - dc.sqrt_beta_t * eg[e]) * inv_sa; en = eg[e]; }
+      else if (pt == DU_PRED_SAMPLE) { x0 = eg[e]; en = (s[e] - dc.sqrt_alpha_t * x0) * inv_sb; }
+      else { x0 = dc.sqrt_alpha_t * s[e] - dc.sqrt_beta_t * eg[e]; en = dc.sqrt_alpha_t * eg[e] + dc.sqrt_beta_t * s[e]; }
+      if (dc.clip_sample) x0 = clamp_nan(x0, -dc.clip_range, dc.clip_range);
+      if (reclip) en = (s[e] - dc.sqrt_alpha_t * x0) * inv_sb;
+      pv[e] = fmaf(dc.sqrt_alpha_prev, x0, dc.dir_coef * en);
+      x0v[e] = x0;
+    }
+    if (FAST) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.prev_out) + b * p.prev_stride + base + 4 * g) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    else store4(p.prev_out, b * p.prev_stride + base + 4 * g, p.prev_dtype, pv);
+    if (p.x0_out) store4(p.x0_out, b * p.x0_stride + base + 4 * g, p.prev_dtype, x0v);
+    if (p.eps_out) store4(p.eps_out, b * p.eps_out_stride + base + 4 * g, DU_F32, eg);
+    if (p.mask_out) store4(p.mask_out, b * p.mask_out_stride + base + 4 * g, DU_F32, mk);
+  }
+}
+
+template <typename T, int MT, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) fused_step_kernel(const __grid_constant__ FusedKParams kp) {
   using FV = Vec16<T>;
   constexpr int VEC = FV::VEC;
   const du_fused_params& p = kp.p;
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned crank = cluster.block_rank();
   const unsigned csize = cluster.num_blocks();
+  const unsigned crank = (csize > 1) ? cluster.block_rank() : 0u;
   const int64_t b = blockIdx.y;
   const int64_t L = kp.L;
   const int64_t base = (int64_t)crank * L;  // slice start within the image
-  const int tid = threadIdx.x, T_ = blockDim.x;
+  const int tid = threadIdx.x;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* u_s = reinterpret_cast<float*>(smem_raw);
-  float* eps_s = u_s + L;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(KEEP_EPS ? (eps_s + L) : eps_s);  // [256] local
-  uint32_t* merged = hist + 256;                                                 // [FUSED_LEVELS][256], used on CTA 0
-  uint32_t* misc = merged + FUSED_LEVELS * 256;                                  // [16]
-  // misc: 0..2 locate result, 3 nan flag (local), 4 min key (CTA0: cluster-wide), 5 nan flag (CTA0: cluster-wide)
+  uint32_t* h0 = reinterpret_cast<uint32_t*>(u_s + L);
+  uint32_t* h1 = h0 + H0_BINS;              // candidate list, or the level-1 / level-2 histograms on the general path
+  uint32_t* misc = h1 + CAND_CAP;
 
-  for (int j = tid; j < 256 * (1 + FUSED_LEVELS); j += T_) hist[j] = 0;
-  if (tid < 16) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
+  for (int j = tid; j < HIST_WORDS; j += THREADS) h0[j] = 0;
+  if (tid < MISC_WORDS) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
   __syncthreads();
-  if (csize > 1) cluster.sync();  // every CTA's shared memory is initialised before any DSMEM access
 
-  uint32_t* merged0 = (csize > 1) ? cluster.map_shared_rank(merged, 0) : merged;
-  uint32_t* misc0 = (csize > 1) ? cluster.map_shared_rank(misc, 0) : misc;
-
+  stamp(kp, 0);
   // ---------------------------------------------------------------- phase A: moments + level-0 histogram
   const int mode = p.moments_mode;
-  const bool centered = (mode == DU_MOM_CENTERED);
-  const bool extra = (mode == DU_MOM_VAR_WITH_CENTER);
-  const int count = p.M + (extra ? 1 : 0);
-  const float cnt = (float)count;
+  const int centre_mode = (mode == DU_MOM_CENTERED) ? 1 : ((mode == DU_MOM_VAR_WITH_CENTER) ? 2 : 0);
+  const int64_t srow = b * p.score_stride + base, erow = b * p.eps_stride + base;
+  float* urow = p.unc_out + b * p.unc_stride + base;
   uint32_t nan_seen = 0;
-  const int centre_mode = centered ? 1 : (extra ? 2 : 0);
-  for (int64_t g = tid; g < L / VEC; g += T_) {
-    const int64_t i = base + g * VEC;
-    float c[VEC], k[VEC], s1[VEC], s2[VEC];
-    uint4 raw_c = make_uint4(0u, 0u, 0u, 0u);
-    if (KEEP_EPS || centre_mode) raw_c = FV::load(p.eps, b * p.eps_stride + i);
-    accumulate_scores<T>(p.scores, p.M, b * p.score_stride + i, raw_c, centre_mode, false, !centered, c, k, s1, s2);
-    if (KEEP_EPS && centre_mode == 0) FV::unpack(raw_c, c);
+  const int ngroups = (int)(L / VEC);
+  for (int g = tid; g < ngroups; g += THREADS) {
     float u[VEC];
+    moments_group<T, MT>(p, srow, erow, (uint32_t)(g * VEC), centre_mode, kp.inv_cnt, kp.inv_cm1, u);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-      if (centered) {
-        u[e] = s2[e] / cnt;
-      } else {
-        float m2 = s2[e] - s1[e] * s1[e] / cnt;
-        m2 = (m2 < 0.0f) ? 0.0f : m2;
-        u[e] = m2 / (float)(count - 1);
-      }
       nan_seen |= (u[e] != u[e]);
-      atomicAdd(&hist[float_to_key(u[e]) >> 24], 1u);
+      atomicAdd(&h0[(__float_as_uint(u[e]) >> (H1_BITS + H2_BITS)) & (H0_BINS - 1)], 1u);
     }
 #pragma unroll
     for (int h = 0; h < VEC / 4; ++h) {
       float4 u4 = make_float4(u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]);
       *reinterpret_cast<float4*>(u_s + g * VEC + 4 * h) = u4;
-      *reinterpret_cast<float4*>(p.unc_out + b * p.unc_stride + i + 4 * h) = u4;
-      if (KEEP_EPS) *reinterpret_cast<float4*>(eps_s + g * VEC + 4 * h) = make_float4(c[4 * h], c[4 * h + 1], c[4 * h + 2], c[4 * h + 3]);
+      *reinterpret_cast<float4*>(urow + g * VEC + 4 * h) = u4;
     }
   }
-  if (__any_sync(0xffffffffu, nan_seen) && (tid & 31) == 0) atomicOr(&misc0[5], 1u);
+  if (__any_sync(0xffffffffu, nan_seen) && (tid & 31) == 0) misc[3] = 1u;
+  if (tid == 0) {  // phase C inputs -> L2 while the select runs
+    prefetch_l2_bulk(reinterpret_cast<const char*>(p.sample) + (b * p.sample_stride + base) * (p.sample_dtype == DU_F32 ? 4 : 2),
+                     (uint32_t)(L * (p.sample_dtype == DU_F32 ? 4 : 2)));
+    prefetch_l2_bulk(reinterpret_cast<const char*>(p.eps) + erow * (int64_t)sizeof(T), (uint32_t)(L * sizeof(T)));
+  }
 
-  // ---------------------------------------------------------------- phase B: radix select over DSMEM
-  uint32_t prefix = 0, pmask = 0, k_rank = kp.lo, below = 0, bincount = 0;
-  for (int level = 0; level < FUSED_LEVELS; ++level) {
-    const int shift = 24 - 8 * level;
-    if (level > 0) {
-      for (int64_t g = tid; g < L / 4; g += T_) {
-        float4 v = *reinterpret_cast<const float4*>(u_s + 4 * g);
-        uint32_t k0 = float_to_key(v.x), k1 = float_to_key(v.y), k2 = float_to_key(v.z), k3 = float_to_key(v.w);
-        if ((k0 & pmask) == prefix) atomicAdd(&hist[(k0 >> shift) & 255u], 1u);
-        if ((k1 & pmask) == prefix) atomicAdd(&hist[(k1 >> shift) & 255u], 1u);
-        if ((k2 & pmask) == prefix) atomicAdd(&hist[(k2 >> shift) & 255u], 1u);
-        if ((k3 & pmask) == prefix) atomicAdd(&hist[(k3 >> shift) & 255u], 1u);
-      }
-    }
-    __syncthreads();
-    const uint32_t* src = hist;
-    if (csize > 1) {
-      if (tid < 256) {
-        uint32_t v = hist[tid];
-        if (v) atomicAdd(&merged0[level * 256 + tid], v);
-      }
-      cluster.sync();
-      src = merged0 + level * 256;
-    }
-    if (tid < 32) locate_bin_256(src, k_rank, misc);
-    __syncthreads();
-    prefix |= misc[0] << shift;
-    pmask |= 255u << shift;
-    below += misc[1];
-    k_rank -= misc[1];
-    bincount = misc[2];
-    __syncthreads();
-    if (level + 1 < FUSED_LEVELS) {
-      if (tid < 256) hist[tid] = 0;
-      __syncthreads();
-    }
-  }
-  const uint32_t key_lo = prefix;
-  uint32_t key_hi = key_lo;
-  if (kp.hi >= below + bincount) {  // cluster-uniform: the hi-th statistic is the smallest key above key_lo
-    uint32_t best = 0xffffffffu;
-    for (int64_t g = tid; g < L / 4; g += T_) {
-      float4 v = *reinterpret_cast<const float4*>(u_s + 4 * g);
-      uint32_t k0 = float_to_key(v.x), k1 = float_to_key(v.y), k2 = float_to_key(v.z), k3 = float_to_key(v.w);
-      if (k0 > key_lo && k0 < best) best = k0;
-      if (k1 > key_lo && k1 < best) best = k1;
-      if (k2 > key_lo && k2 < best) best = k2;
-      if (k3 > key_lo && k3 < best) best = k3;
-    }
-    best = __reduce_min_sync(0xffffffffu, best);
-    if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc0[4], best);
-  }
-  if (csize > 1) cluster.sync(); else __syncthreads();
-  if (kp.hi >= below + bincount) key_hi = misc0[4];
-  const bool has_nan = misc0[5] != 0;
-  float thr = lerp_torch(key_to_float(key_lo), key_to_float(key_hi), kp.w, p.lerp_fma);
-  if (has_nan) thr = __int_as_float(0x7fc00000);
+  stamp(kp, 1);
+  // ---------------------------------------------------------------- phase B: exact per-image threshold
+  const float thr = select_threshold<THREADS>(cluster, csize, crank, kp, u_s, h0, h1, misc);
+  stamp(kp, 5);
   if (crank == 0 && tid == 0 && p.thr_out) p.thr_out[b] = thr;
 
   // ---------------------------------------------------------------- phase C: mask + posterior + DDIM
-  du_ddim_coeffs dc = p.ddim;
-  dc.add_noise = 0;
-  const bool higher = p.higher != 0;
-  constexpr int UNR = 2;  // groups per thread per trip: all global loads of a trip are issued before the arithmetic
-  for (int64_t g0 = tid; g0 < L / 4; g0 += (int64_t)UNR * T_) {
-    float s[UNR][4], S[UNR][4], e0[UNR][4];
-#pragma unroll
-    for (int r = 0; r < UNR; ++r) {
-      const int64_t g = g0 + (int64_t)r * T_;
-      if (g < L / 4) {
-        const int64_t i = base + 4 * g;
-        load4(p.sample, b * p.sample_stride + i, p.sample_dtype, s[r]);
-        if (!KEEP_EPS) load4(p.eps, b * p.eps_stride + i, p.score_dtype, e0[r]);
-        if (p.S) {
-          float4 s4 = __ldg(reinterpret_cast<const float4*>(p.S + (p.S_broadcast ? 0 : b * p.S_stride) + i));
-          S[r][0] = s4.x; S[r][1] = s4.y; S[r][2] = s4.z; S[r][3] = s4.w;
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < UNR; ++r) {
-      const int64_t g = g0 + (int64_t)r * T_;
-      if (g >= L / 4) break;
-      const int64_t i = base + 4 * g;
-      float4 u4 = *reinterpret_cast<const float4*>(u_s + 4 * g);
-      float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-      if (KEEP_EPS) {
-        float4 e4 = *reinterpret_cast<const float4*>(eps_s + 4 * g);
-        e0[r][0] = e4.x; e0[r][1] = e4.y; e0[r][2] = e4.z; e0[r][3] = e4.w;
-      }
-      if (!p.S) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) S[r][e] = e0[r][e];
-      }
-      float pv[4], x0v[4], eg[4], mk[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        mk[e] = (higher ? (uu[e] > thr) : (uu[e] < thr)) ? 1.0f : 0.0f;
-        float inv_var = __fdiv_rn(1.0f, uu[e]);
-        float trace = __fadd_rn(__fmul_rn(p.post_M, inv_var), p.inv_alpha_hat);
-        float prec = __fdiv_rn(1.0f, trace);
-        float post = __fmul_rn(prec, __fmul_rn(inv_var, S[r][e]));
-        eg[e] = __fadd_rn(__fmul_rn(e0[r][e], __fsub_rn(1.0f, mk[e])), __fmul_rn(mk[e], post));
-        DdimOut o = ddim_update(eg[e], s[r][e], 0.0f, dc);
-        pv[e] = o.prev; x0v[e] = o.x0;
-      }
-      store4(p.prev_out, b * p.prev_stride + i, p.prev_dtype, pv);
-      if (p.x0_out) store4(p.x0_out, b * p.x0_stride + i, p.prev_dtype, x0v);
-      if (p.eps_out) store4(p.eps_out, b * p.eps_out_stride + i, DU_F32, eg);
-      if (p.mask_out) store4(p.mask_out, b * p.mask_out_stride + i, DU_F32, mk);
-    }
-  }
-  if (csize > 1) cluster.sync();  // keep CTA 0's shared memory alive until every peer has read it
+  const bool fast_c = p.ddim.prediction_type == DU_PRED_EPSILON && !p.ddim.use_clipped_model_output &&
+                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32;
+  if (fast_c) guided_update_slice<T, THREADS, true>(kp, u_s, thr, b, base);
+  else guided_update_slice<T, THREADS, false>(kp, u_s, thr, b, base);
+  stamp(kp, 6);
+  // peers may still be reading this CTA's histograms: do not exit before they are past their last DSMEM read
+  if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 
-static size_t fused_smem_bytes(int64_t L, bool keep_eps) {
-  return (size_t)L * 4 * (keep_eps ? 2 : 1) + (size_t)(256 * (1 + FUSED_LEVELS) + 16) * 4;
-}
+static size_t fused_smem_bytes(int64_t L) { return (size_t)L * 4 + (size_t)(HIST_WORDS + MISC_WORDS) * 4; }
 
-struct FusedPlan { int cluster; bool keep_eps; int threads; size_t smem; };
+struct FusedPlan { int cluster; int threads; int minb; size_t smem; };
 
 static bool fused_plan(int64_t n, int vec, FusedPlan* out) {
-  // override for tuning: DU_FUSED_CLUSTER=<1|2|4|8>, DU_FUSED_KEEP_EPS=<0|1>, DU_FUSED_THREADS=<n>
+  // override for tuning: DU_FUSED_CLUSTER=<1|2|4|8>, DU_FUSED_THREADS=<256|512|1024>
   const char* e_c = getenv("DU_FUSED_CLUSTER");
-  const char* e_k = getenv("DU_FUSED_KEEP_EPS");
   const char* e_t = getenv("DU_FUSED_THREADS");
   const size_t kMax = 227 * 1024, kHalf = 113 * 1024;
-  int best_c = 0; bool best_keep = false;
-  for (int pass = 0; pass < 2 && !best_c; ++pass) {      // pass 0: two CTAs per SM; pass 1: anything that fits
-    for (int keep = 1; keep >= 0 && !best_c; --keep) {
-      for (int c = 1; c <= 8; c <<= 1) {
-        if (e_c && atoi(e_c) != c) continue;
-        if (e_k && atoi(e_k) != keep) continue;
-        if (n % ((int64_t)c * vec) != 0) continue;
-        size_t s = fused_smem_bytes(n / c, keep != 0);
-        if (s <= (pass == 0 ? kHalf : kMax)) { best_c = c; best_keep = keep != 0; break; }
-      }
+  int best_c = 0;
+  for (int pass = 0; pass < 2 && !best_c; ++pass) {  // pass 0: two CTAs per SM; pass 1: anything that fits
+    for (int c = 1; c <= MAX_CLUSTER; c <<= 1) {
+      if (e_c && atoi(e_c) != c) continue;
+      if (n % ((int64_t)c * vec) != 0) continue;
+      if (fused_smem_bytes(n / c) <= (pass == 0 ? kHalf : kMax)) { best_c = c; break; }
     }
   }
   if (!best_c) return false;
-  int64_t L = n / best_c;
-  int64_t groups = L / vec;
-  int threads = (groups >= 1024) ? 512 : 256;  // the histogram merge uses threads 0..255
-  if (e_t) threads = (atoi(e_t) == 512) ? 512 : 256;
-  out->cluster = best_c; out->keep_eps = best_keep; out->threads = threads; out->smem = fused_smem_bytes(L, best_keep);
+  const int64_t L = n / best_c;
+  const size_t smem = fused_smem_bytes(L);
+  const int64_t groups = L / vec;
+  int threads = (groups >= 2048) ? 512 : 256;
+  if (e_t) { int t = atoi(e_t); threads = (t == 1024 || t == 512) ? t : 256; }
+  if (threads == 1024 && smem > kHalf) { /* one CTA per SM anyway */ }
+  out->cluster = best_c; out->threads = threads; out->smem = smem;
+  out->minb = (threads == 1024) ? 1 : 2;
   return true;
 }
 
-template <typename T, bool KEEP, int THREADS>
+template <typename T, int MT, int THREADS, int MINB>
 static int launch_fused_t(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
-  auto kern = fused_step_kernel<T, KEEP, THREADS>;
+  auto kern = fused_step_kernel<T, MT, THREADS, MINB>;
   DU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)plan.cluster, (unsigned)kp.p.B, 1);
-  cfg.blockDim = dim3((unsigned)plan.threads);
+  cfg.blockDim = dim3((unsigned)THREADS);
   cfg.dynamicSmemBytes = plan.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -286,10 +549,22 @@ static int launch_fused_t(const FusedKParams& kp, const FusedPlan& plan, cudaStr
   return DU_OK;
 }
 
-template <typename T, bool KEEP>
+template <typename T, int MT>
+static int launch_fused_m(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
+  if (plan.threads == 1024) return launch_fused_t<T, MT, 1024, 1>(kp, plan, st);
+  if (plan.threads == 512) return launch_fused_t<T, MT, 512, 2>(kp, plan, st);
+  return launch_fused_t<T, MT, 256, 2>(kp, plan, st);
+}
+
+template <typename T>
 static int launch_fused(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
-  if (plan.threads == 512) return launch_fused_t<T, KEEP, 512>(kp, plan, st);
-  return launch_fused_t<T, KEEP, 256>(kp, plan, st);
+  switch (kp.p.M) {  // the BASELINE configurations get all their loads in flight at once; any other M runs the batched loop
+    case 4: return launch_fused_m<T, 4>(kp, plan, st);
+    case 5: return launch_fused_m<T, 5>(kp, plan, st);
+    case 8: return launch_fused_m<T, 8>(kp, plan, st);
+    case 16: return launch_fused_m<T, 16>(kp, plan, st);
+    default: return launch_fused_m<T, 0>(kp, plan, st);
+  }
 }
 
 }  // namespace du
@@ -321,7 +596,8 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
     return set_error(DU_ERR_TOO_LARGE, "du_fused_uncertainty_step: rows of %lld elements do not fit cluster shared memory; use the unfused calls", (long long)p->n);
   // 128-bit access requirements
   bool ok = aligned(p->eps, 16) && (p->eps_stride % vec == 0) && (p->score_stride % vec == 0) &&
-            vec4_ok(p->sample, p->sample_stride, p->sample_dtype) && aligned(p->unc_out, 16) && (p->unc_stride % 4 == 0) &&
+            aligned(p->sample, 16) && (p->sample_stride % (p->sample_dtype == DU_F32 ? 4 : 8) == 0) &&
+            aligned(p->unc_out, 16) && (p->unc_stride % 4 == 0) &&
             vec4_ok(p->prev_out, p->prev_stride, p->prev_dtype) && vec4_ok(p->x0_out, p->x0_stride, p->prev_dtype) &&
             vec4_ok(p->eps_out, p->eps_out_stride, DU_F32) && vec4_ok(p->mask_out, p->mask_out_stride, DU_F32) &&
             (!p->S || (aligned(p->S, 16) && (p->S_broadcast || p->S_stride % 4 == 0)));
@@ -338,10 +614,37 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
   kp.lo = (uint32_t)fl;
   kp.hi = (uint32_t)ceilf(rank);
   kp.w = rank - fl;
+  const int count = p->M + (p->moments_mode == DU_MOM_VAR_WITH_CENTER ? 1 : 0);
+  kp.inv_cnt = 1.0f / (float)count;
+  kp.inv_cm1 = 1.0f / (float)(count - 1);  // count == 1 -> inf; 0 * inf = NaN like torch.var
+  kp.inv_sqrt_alpha_t = 1.0f / p->ddim.sqrt_alpha_t;
+  kp.timeline = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (p->score_dtype) {
-    case DU_F32: return plan.keep_eps ? launch_fused<float, true>(kp, plan, st) : launch_fused<float, false>(kp, plan, st);
-    case DU_F16: return plan.keep_eps ? launch_fused<__half, true>(kp, plan, st) : launch_fused<__half, false>(kp, plan, st);
-    default: return plan.keep_eps ? launch_fused<__nv_bfloat16, true>(kp, plan, st) : launch_fused<__nv_bfloat16, false>(kp, plan, st);
+  const char* tl_path = getenv("DU_FUSED_TIMELINE");  // debug only: synchronises and writes the per-CTA phase stamps
+  const size_t tl_words = (size_t)p->B * plan.cluster * 8;
+  if (tl_path) {
+    DU_CUDA(cudaMalloc(&kp.timeline, tl_words * 8));
+    DU_CUDA(cudaMemsetAsync(kp.timeline, 0, tl_words * 8, st));
   }
+  int rc;
+  switch (p->score_dtype) {
+    case DU_F32: rc = launch_fused<float>(kp, plan, st); break;
+    case DU_F16: rc = launch_fused<__half>(kp, plan, st); break;
+    default: rc = launch_fused<__nv_bfloat16>(kp, plan, st); break;
+  }
+  if (tl_path) {
+    unsigned long long* h = (unsigned long long*)malloc(tl_words * 8);
+    cudaMemcpyAsync(h, kp.timeline, tl_words * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    FILE* f = fopen(tl_path, "w");
+    if (f) {
+      for (size_t c = 0; c < tl_words / 8; ++c) {
+        for (int k = 0; k < 8; ++k) fprintf(f, "%llu%c", h[c * 8 + k], k == 7 ? '\n' : ' ');
+      }
+      fclose(f);
+    }
+    free(h);
+    cudaFree(kp.timeline);
+  }
+  return rc;
 }

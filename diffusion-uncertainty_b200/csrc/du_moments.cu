@@ -24,6 +24,7 @@ struct MomentsParams {
   int64_t unc_stride;
   float* mean;
   int64_t mean_stride;
+  float inv_cnt, inv_cm1;  // 1/count and 1/(count-1) (count == 1 -> inf: 0 * inf = NaN like torch.var)
 };
 
 // Accumulator for one element.
@@ -33,21 +34,21 @@ struct Acc {
   float s2;  // sum of d^2
 };
 
-__device__ __forceinline__ float finish(const Acc& a, int mode, bool centered, int count, float* mean_out) {
-  float cnt = (float)count;
-  if (mean_out) *mean_out = a.k + a.s1 / cnt;
-  if (mode == DU_MOM_CENTERED || mode == DU_MOM_RAW) return a.s2 / cnt;
+// reciprocal-multiply instead of IEEE division (<= 1 ulp apart; the kernel is issue-bound otherwise), the same
+// expressions as the fused step so that both paths produce the same bits
+__device__ __forceinline__ float finish(const Acc& a, int mode, bool centered, float inv_cnt, float inv_cm1, float* mean_out) {
+  if (mean_out) *mean_out = fmaf(a.s1, inv_cnt, a.k);
+  if (mode == DU_MOM_CENTERED || mode == DU_MOM_RAW) return fmaf(a.s2, inv_cnt, 0.0f);
   if (mode == DU_MOM_PARTIAL_M2 && centered) return a.s2;
-  float m2 = a.s2 - a.s1 * a.s1 / cnt;  // sum of squared deviations about the mean (shifted-data form)
-  m2 = (m2 < 0.0f) ? 0.0f : m2;         // (NaN compares false and is kept)
+  const float m2 = m2_from_sums(a.s1, a.s2, inv_cnt);  // sum of squared deviations about the mean (shifted-data form)
   if (mode == DU_MOM_PARTIAL_M2) return m2;
-  float var = m2 / (float)(count - 1);  // count == 1 -> 0/0 = NaN like torch.var
+  const float var = fmaf(m2, inv_cm1, 0.0f);
   return mode == DU_MOM_STD_UNBIASED ? sqrtf(var) : var;
 }
 
 // kernel: grid.x covers a row in groups of VEC elements, grid.y strides over images.
 // VECTOR = false is the scalar fallback for unaligned / ragged views.
-template <typename T, bool VECTOR>
+template <typename T, bool VECTOR, int MT>
 __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ MomentsParams p) {
   using SV = Vec16<T>;
   constexpr int VEC = VECTOR ? SV::VEC : 1;
@@ -56,7 +57,6 @@ __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ Mo
   const bool centered = (mode == DU_MOM_CENTERED) || (mode == DU_MOM_PARTIAL_M2 && p.center != nullptr);
   const bool shifted = !(centered || mode == DU_MOM_RAW);
   const bool extra = (mode == DU_MOM_VAR_WITH_CENTER);
-  const int count = p.M + (extra ? 1 : 0);
 
   for (int64_t b = blockIdx.y; b < p.B; b += gridDim.y) {
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ Mo
 #pragma unroll
           for (int e = 0; e < VEC; ++e) c[e] = load1(p.center, b * p.center_stride + i + e, p.center_dtype);
         }
-        accumulate_scores<T>(p.scores, p.M, b * p.score_stride + i, raw_c, centre_mode, !same_dt, shifted, c, k, s1, s2);
+        if constexpr (MT > 0) accumulate_scores_ct<T, MT>(p.scores, b * p.score_stride, (uint32_t)i * (uint32_t)sizeof(T), raw_c, centre_mode, !same_dt, shifted, c, k, s1, s2);
+        else accumulate_scores<T>(p.scores, p.M, b * p.score_stride + i, raw_c, centre_mode, !same_dt, shifted, c, k, s1, s2);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { acc[e].k = k[e]; acc[e].s1 = s1[e]; acc[e].s2 = s2[e]; }
       } else {
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ Mo
       }
       float u[VEC], mu[VEC];
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) u[e] = finish(acc[e], mode, centered, count, p.mean ? &mu[e] : nullptr);
+      for (int e = 0; e < VEC; ++e) u[e] = finish(acc[e], mode, centered, p.inv_cnt, p.inv_cm1, p.mean ? &mu[e] : nullptr);
 
       if constexpr (VECTOR) {
 #pragma unroll
@@ -122,8 +123,14 @@ static int launch_moments(const MomentsParams& p, bool vec, cudaStream_t st) {
   const int threads = 256;
   int64_t groups = vec ? (p.n / VEC) : p.n;
   RowGrid g = row_grid(p.B, groups, threads);
-  if (vec) moments_kernel<T, true><<<g.grid, g.block, 0, st>>>(p);
-  else moments_kernel<T, false><<<g.grid, g.block, 0, st>>>(p);
+  if (!vec) moments_kernel<T, false, 0><<<g.grid, g.block, 0, st>>>(p);
+  else switch (p.M) {  // compile-time M for the BASELINE sample counts, batched runtime-M loop otherwise
+    case 4: moments_kernel<T, true, 4><<<g.grid, g.block, 0, st>>>(p); break;
+    case 5: moments_kernel<T, true, 5><<<g.grid, g.block, 0, st>>>(p); break;
+    case 8: moments_kernel<T, true, 8><<<g.grid, g.block, 0, st>>>(p); break;
+    case 16: moments_kernel<T, true, 16><<<g.grid, g.block, 0, st>>>(p); break;
+    default: moments_kernel<T, true, 0><<<g.grid, g.block, 0, st>>>(p); break;
+  }
   DU_LAUNCH_CHECK("moments_kernel");
   return DU_OK;
 }
@@ -202,6 +209,9 @@ extern "C" int du_moments(const void* const* scores, int M, int64_t score_stride
   p.unc = unc_out; p.unc_stride = unc_stride; p.unc_dtype = unc_dtype;
   p.mean = mean_out; p.mean_stride = mean_stride;
   p.B = B; p.n = n;
+  const int count = M + (mode == DU_MOM_VAR_WITH_CENTER ? 1 : 0);
+  p.inv_cnt = 1.0f / (float)count;
+  p.inv_cm1 = 1.0f / (float)(count - 1);
   cudaStream_t st = (cudaStream_t)stream;
   switch (score_dtype) {
     case DU_F32: return launch_moments<float>(p, vec_ok, st);

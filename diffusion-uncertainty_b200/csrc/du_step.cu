@@ -227,6 +227,26 @@ struct CopyF {
   }
 };
 
+// ---- uint8 image epilogue: (x/2 + 0.5).clamp(0,1) * 255 -> round (half to even) -> uint8 ----------------------------
+struct ImageU8F {
+  const void* x; int64_t x_stride; int x_dtype;
+  uint8_t* out; int64_t out_stride;
+  template <int VEC> __device__ __forceinline__ void run(int64_t b, int64_t i) const {
+    float v[VEC];
+    loadv<VEC>(x, b * x_stride + i, x_dtype, v);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = __fadd_rn(__fmul_rn(v[e], 0.5f), 0.5f);
+      t = fminf(fmaxf(t, 0.0f), 1.0f);                 // NaN -> 0 here; torch's NaN -> uint8 cast is undefined anyway
+      const uint32_t q = (uint32_t)__float2int_rn(__fmul_rn(t, 255.0f));
+      if constexpr (VEC == 4) packed |= q << (8 * e);
+      else out[b * out_stride + i] = (uint8_t)q;
+    }
+    if constexpr (VEC == 4) *reinterpret_cast<uint32_t*>(out + b * out_stride + i) = packed;
+  }
+};
+
 // ---- batch-axis sum (fp64 accumulation, deterministic) --------------------------------------------------
 __global__ void __launch_bounds__(256) batch_sum_kernel(const void* x, int64_t stride, int dt, int64_t B, int64_t n, float* out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -244,52 +264,61 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const void* x, int64_t s
   }
 }
 
-// Vector form: a cluster of BS_SPLIT CTAs shares one block of columns, each CTA sums a contiguous range of
-// images (16 B loads, 8 in flight per thread); the fp64 partials meet in CTA 0's shared memory through DSMEM
-// and are added in rank order, so the result does not depend on scheduling.
+// Vector form: one CTA owns 32 x 16-byte column groups (512 contiguous bytes per image); its BS_SPLIT warps each sum a
+// contiguous range of images (8 loads of 16 B in flight per thread), the fp64 partials meet in shared memory and are added
+// in warp order, so the result does not depend on scheduling.
 constexpr int BS_SPLIT = 8;
-constexpr int BS_THREADS = 128;
 
-__global__ void __cluster_dims__(1, BS_SPLIT, 1) __launch_bounds__(BS_THREADS)
-batch_sum_cluster_kernel(const void* x, int64_t stride, int dt, int64_t B, int64_t n, float* out) {
-  cg::cluster_group cluster = cg::this_cluster();
-  __shared__ double part[BS_THREADS * 4];
-  const unsigned r = cluster.block_rank();
+template <typename T>
+__global__ void __launch_bounds__(32 * BS_SPLIT) batch_sum_rows_kernel(const T* __restrict__ x, int64_t stride, int64_t B, int64_t n,
+                                                                       float* __restrict__ out) {
+  using V = Vec16<T>;
+  constexpr int VEC = V::VEC;
+  __shared__ double part[BS_SPLIT][32][VEC];
+  const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
   const int64_t per = (B + BS_SPLIT - 1) / BS_SPLIT;
   const int64_t b0 = r * per, b1 = (b0 + per < B) ? b0 + per : B;
-  const int64_t i = ((int64_t)blockIdx.x * BS_THREADS + threadIdx.x) * 4;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t i = ((int64_t)blockIdx.x * 32 + lane) * VEC;
+  double acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.0;
   if (i < n) {
+    const T* col = x + i;
     int64_t b = b0;
     for (; b + 8 <= b1; b += 8) {
-      float v[8][4];
+      uint4 raw[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) load4(x, (b + j) * stride + i, dt, v[j]);
+      for (int j = 0; j < 8; ++j) raw[j] = ldg_stream_128(col + (b + j) * stride);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j) {
+        float v[VEC];
+        V::unpack(raw[j], v);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] += (double)v[j][e];
+        for (int e = 0; e < VEC; ++e) acc[e] += (double)v[e];
+      }
     }
     for (; b < b1; ++b) {
-      float v[4];
-      load4(x, b * stride + i, dt, v);
+      float v[VEC];
+      V::unpack(ldg_stream_128(col + b * stride), v);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] += (double)v[e];
+      for (int e = 0; e < VEC; ++e) acc[e] += (double)v[e];
     }
   }
 #pragma unroll
-  for (int e = 0; e < 4; ++e) part[threadIdx.x * 4 + e] = acc[e];
-  cluster.sync();
+  for (int e = 0; e < VEC; ++e) part[r][lane][e] = acc[e];
+  __syncthreads();
   if (r == 0 && i < n) {
-    double t[4] = {0.0, 0.0, 0.0, 0.0};
-    for (unsigned k = 0; k < BS_SPLIT; ++k) {
-      const double* p = cluster.map_shared_rank(part, k);
+    float t[VEC];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) t[e] += p[threadIdx.x * 4 + e];
+    for (int e = 0; e < VEC; ++e) {
+      double a = 0.0;
+#pragma unroll
+      for (int k = 0; k < BS_SPLIT; ++k) a += part[k][lane][e];
+      t[e] = (float)a;
     }
-    *reinterpret_cast<float4*>(out + i) = make_float4((float)t[0], (float)t[1], (float)t[2], (float)t[3]);
+#pragma unroll
+    for (int h = 0; h < VEC / 4; ++h) *reinterpret_cast<float4*>(out + i + 4 * h) = make_float4(t[4 * h], t[4 * h + 1], t[4 * h + 2], t[4 * h + 3]);
   }
-  cluster.sync();  // peers' shared memory stays alive until CTA 0 has read it
 }
 
 // ---- z-norm statistics: fp64 (count, sum, sum of squares about a pivot) per block, fixed-order final merge -
@@ -479,10 +508,14 @@ extern "C" int du_guided_step(const du_guided_params* p, du_stream_t stream) {
 extern "C" int du_batch_sum(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, float* out, du_stream_t stream) {
   if (!check_view(x, x_dtype) || !out || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_batch_sum: bad arguments");
   if (n == 0) return DU_OK;
-  if (B >= 2 * BS_SPLIT && n % 4 == 0 && vec4_ok(x, x_stride, x_dtype) && aligned(out, 16)) {
-    dim3 grid((unsigned)((n / 4 + BS_THREADS - 1) / BS_THREADS), BS_SPLIT);
-    batch_sum_cluster_kernel<<<grid, BS_THREADS, 0, (cudaStream_t)stream>>>(x, x_stride, x_dtype, B, n, out);
-    DU_LAUNCH_CHECK("batch_sum_cluster_kernel");
+  const int vec = (x_dtype == DU_F32) ? 4 : 8;
+  if (B >= 2 * BS_SPLIT && n % vec == 0 && aligned(x, 16) && x_stride % vec == 0 && aligned(out, 16)) {
+    const unsigned grid = (unsigned)((n / vec + 31) / 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dtype == DU_F32) batch_sum_rows_kernel<float><<<grid, 32 * BS_SPLIT, 0, st>>>((const float*)x, x_stride, B, n, out);
+    else if (x_dtype == DU_F16) batch_sum_rows_kernel<__half><<<grid, 32 * BS_SPLIT, 0, st>>>((const __half*)x, x_stride, B, n, out);
+    else batch_sum_rows_kernel<__nv_bfloat16><<<grid, 32 * BS_SPLIT, 0, st>>>((const __nv_bfloat16*)x, x_stride, B, n, out);
+    DU_LAUNCH_CHECK("batch_sum_rows_kernel");
     return DU_OK;
   }
   int64_t blocks = (n + 255) / 256;
@@ -498,6 +531,14 @@ extern "C" int du_perturb(const void* x, int64_t x_stride, int x_dtype, const vo
     return set_error(DU_ERR_BAD_ARG, "du_perturb: bad arguments");
   PerturbF f{x, x_stride, x_dtype, noise, noise_stride, noise_dtype, a, b, out, out_stride, out_dtype};
   bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && vec4_ok(noise, noise_stride, noise_dtype) && vec4_ok(out, out_stride, out_dtype);
+  return launch_rows(B, n, vec, f, (cudaStream_t)stream);
+}
+
+extern "C" int du_image_uint8(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, uint8_t* out,
+                              int64_t out_stride, du_stream_t stream) {
+  if (!check_view(x, x_dtype) || !out || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_image_uint8: bad arguments");
+  ImageU8F f{x, x_stride, x_dtype, out, out_stride};
+  bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && aligned(out, 4) && (out_stride % 4 == 0);
   return launch_rows(B, n, vec, f, (cudaStream_t)stream);
 }
 

@@ -1,0 +1,108 @@
+"""L4 sampling loop with device-side uncertainty-map accumulation — drop-in for
+`generate_samples_model_scheduler_class_conditioned_from_tensor` (diffusion_uncertainty/generate_samples.py:125-231).
+
+What changes relative to the reference loop is only where the per-step outputs go:
+  reference  `uncertanties.append(output.uncertainty.cpu())` / `scores.append(output.pred_epsilon.cpu())` every in-window
+             step (synchronous pageable D2H), `torch.stack(dim=1)` per batch, `torch.cat(dim=0)` over batches (:189-201, 229-231)
+  here       the scheduler's moments kernel writes each map straight into slot [:, k] of a device `[B, T_uc, C, H, W]`
+             buffer, the score goes there with one du_accumulate_slot launch, and each batch leaves the GPU as ONE async
+             copy into its slice of a pinned `[N, T_uc, C, H, W]` host tensor — the final result, no stack / cat.
+The model call, the timestep loop and the returned dict (`gen_images` uint8, `uncertainty`, `score`, `intermediates`, `fid`)
+are the reference's.
+"""
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import torch
+
+from . import ops
+from .accumulate import UncertaintyMapAccumulator
+from .schedulers_uncertainty.mixin import SchedulerUncertaintyMixin
+
+
+def predict_model(model, x, t_tensor, y):
+    """ADM call convention of the reference loops (generate_samples.py:186): learned-sigma head dropped."""
+    return model(x, t_tensor, y=y)[:, :3]
+
+
+@torch.no_grad()
+def generate_samples_model_scheduler_class_conditioned_from_tensor(X_T: torch.Tensor, y: torch.Tensor, batch_size: int,
+                                                                   device: torch.device, model: torch.nn.Module, scheduler,
+                                                                   fid_evaluator: Any = None, save_intermediates: bool = False):
+    assert X_T.shape[0] == y.shape[0], f"{X_T.shape=} {y.shape=}"
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"device {device}: the uncertainty path has no CPU fallback")
+    num_samples = X_T.shape[0]
+    with_unc = isinstance(scheduler, SchedulerUncertaintyMixin)
+    n_steps = len(scheduler.timesteps)
+
+    host_unc = host_score = None
+    copies = []
+    images, intermediates_all = [], []
+    start = 0
+    while start < num_samples:
+        stop = min(start + batch_size, num_samples)
+        x = X_T[start:stop].to(device)
+        y_batch = y[start:stop].to(device)
+        B = stop - start
+        scheduler.set_timesteps(n_steps)
+        acc_u = acc_s = None
+        if with_unc:
+            scheduler.prompt_embeds = y_batch
+            t_uc = len(scheduler.uncertainty_timesteps()) if hasattr(scheduler, "uncertainty_timesteps") else sum(
+                1 for t in scheduler.timesteps.tolist() if scheduler.timestep_after_step >= t >= scheduler.timestep_end_step)
+            if t_uc > 0:
+                acc_u = UncertaintyMapAccumulator(B, t_uc, x.shape[1:], device)
+                acc_s = UncertaintyMapAccumulator(B, t_uc, x.shape[1:], device)
+                if hasattr(scheduler, "attach_accumulator"):
+                    scheduler.attach_accumulator(acc_u)
+        inter = []
+        host_copies = getattr(scheduler, "host_copies", False)
+        if host_copies:
+            scheduler.host_copies = False      # MC-dropout's per-step .cpu() of x0 / score (mc_dropout.py:551-554): not in this loop
+        try:
+            for t in scheduler.timesteps.tolist():
+                t_tensor = torch.full((B,), t, device=device, dtype=torch.long)
+                x = scheduler.scale_model_input(x, t)
+                noisy_residual = predict_model(model, x, t_tensor, y_batch)
+                output = scheduler.step(noisy_residual, t, x)
+                if save_intermediates:
+                    inter.append(output.prev_sample)
+                if with_unc and scheduler.timestep_after_step >= t >= scheduler.timestep_end_step:
+                    if getattr(scheduler, "map_sink", None) is None:     # a scheduler that cannot write into the sink itself
+                        acc_u.stash(output.uncertainty)
+                    acc_s.stash(output.pred_epsilon)
+                x = output.prev_sample
+        finally:
+            if host_copies:
+                scheduler.host_copies = True
+            if with_unc and hasattr(scheduler, "attach_accumulator"):
+                scheduler.attach_accumulator(None)
+        if acc_u is not None:
+            if host_unc is None:
+                shape = (num_samples, acc_u.num_slots) + tuple(x.shape[1:])
+                host_unc = torch.empty(shape, dtype=acc_u.buffer.dtype, pin_memory=True)
+                host_score = torch.empty(shape, dtype=acc_s.buffer.dtype, pin_memory=True)
+            copies.append(acc_u.to_host_async(host_unc[start:stop])[1])
+            copies.append(acc_s.to_host_async(host_score[start:stop])[1])
+        gen = ops.image_uint8(x)          # (x/2 + .5).clamp(0,1)*255 -> round -> uint8 (:203-212), one launch
+        if fid_evaluator is not None:
+            fid_evaluator.update(gen, real=False)
+        images.append(gen)
+        if save_intermediates:
+            intermediates_all.append(torch.stack(inter, dim=1))
+        start = stop
+
+    results = {"gen_images": torch.cat(images, dim=0).cpu()}
+    if save_intermediates:
+        results["intermediates"] = torch.cat(intermediates_all, dim=0).cpu()
+    if fid_evaluator is not None:
+        results["fid"] = fid_evaluator.compute()
+    if host_unc is not None:
+        for ev in copies:
+            ev.synchronize()
+        results["uncertainty"] = host_unc
+        results["score"] = host_score
+    return results

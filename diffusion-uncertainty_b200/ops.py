@@ -372,6 +372,15 @@ def accumulate_slot(src: torch.Tensor, dst_slot: torch.Tensor):
     _count()
 
 
+def image_uint8(x: torch.Tensor) -> torch.Tensor:
+    """uint8 images from samples in [-1, 1]: (x/2 + 0.5).clamp(0,1) * 255, rounded half to even (du_image_uint8)."""
+    r = Rows(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    L.check(L.load().du_image_uint8(r.ptr, r.stride, r.dt, r.B, r.n, C.c_void_p(out.data_ptr()), r.n, _stream(x)))
+    _count()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ whole step
 def fused_supported(n: int, dtype: torch.dtype) -> int:
     """Cluster size the fused kernel would use for rows of n elements (0 = not supported)."""

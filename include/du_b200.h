@@ -225,6 +225,13 @@ int du_accumulate_slot(const void* src, int64_t src_stride, int src_dtype, int64
                        void* dst, int64_t dst_stride, int dst_dtype, du_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Image epilogue of the sampling loops: out = uint8(round((x/2 + 0.5).clamp(0,1) * 255)),
+ * round half to even like torch.round.  generate_samples.py:203-215.
+ * ---------------------------------------------------------------------------------------------- */
+int du_image_uint8(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, uint8_t* out,
+                   int64_t out_stride, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The fused uncertainty step: F1 -> F2a -> F5 -> F3 (+F8) in ONE launch.  One thread-block cluster per
  * image keeps the image's map (and eps) in distributed shared memory, selects the two order
  * statistics there, and applies the guided DDIM update, so HBM sees each input and output once
