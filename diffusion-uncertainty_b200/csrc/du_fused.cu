@@ -47,6 +47,8 @@ struct FusedKParams {
   uint32_t lo, hi;  // ranks
   float w;          // lerp weight
   float inv_cnt, inv_cm1, inv_sqrt_alpha_t;
+  uint32_t late_from;   // CTAs whose linear index is >= late_from start their streaming phase late_ns later (0 = off)
+  uint32_t late_ns;
   unsigned long long* timeline;  // debug (DU_FUSED_TIMELINE): [CTA][8] globaltimer stamps at the phase boundaries, else null
 };
 
@@ -204,31 +206,13 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
   float thr;
 
   if (cnt0 <= (uint32_t)CAND_CAP) {
-    // ---- compaction, warp-aggregated: one shared-memory atomic per warp and trip (a single list cursor hit by every
-    // matching lane serialises), lanes place their keys behind the warp's reservation by an intra-warp prefix count
-    const int lane = tid & 31;
-    const int trips = (ng4 + THREADS - 1) / THREADS;
-#pragma unroll 2
-    for (int it = 0; it < trips; ++it) {
-      const int g = it * THREADS + tid;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      bool m0 = false, m1 = false, m2 = false, m3 = false;
-      if (g < ng4) {
-        v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
-        m0 = (v.x & msk0) == want; m1 = (v.y & msk0) == want; m2 = (v.z & msk0) == want; m3 = (v.w & msk0) == want;
-      }
-      const uint32_t mine = (uint32_t)m0 + (uint32_t)m1 + (uint32_t)m2 + (uint32_t)m3;
-      if (__any_sync(0xffffffffu, mine != 0)) {
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        uint32_t base_slot = 0;
-        if (lane == 31) base_slot = atomicAdd(&misc[6], incl);
-        base_slot = __shfl_sync(0xffffffffu, base_slot, 31);
-        uint32_t slot = base_slot + incl - mine;
+    // ---- compaction: one branch per 4 elements (a warp-aggregated cursor was measured slower: the pass is issue-bound)
+#pragma unroll 4
+    for (int g = tid; g < ng4; g += THREADS) {
+      const uint4 v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
+      const bool m0 = (v.x & msk0) == want, m1 = (v.y & msk0) == want, m2 = (v.z & msk0) == want, m3 = (v.w & msk0) == want;
+      if (m0 | m1 | m2 | m3) {
+        uint32_t slot = atomicAdd(&misc[6], (uint32_t)m0 + (uint32_t)m1 + (uint32_t)m2 + (uint32_t)m3);
         if (m0) work[slot++] = v.x & 0x7fffffffu;
         if (m1) work[slot++] = v.y & 0x7fffffffu;
         if (m2) work[slot++] = v.z & 0x7fffffffu;
@@ -454,6 +438,17 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_step_kernel(const __grid_
   if (tid < MISC_WORDS) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
   __syncthreads();
 
+  // Two CTAs share an SM and would otherwise run the three phases in lockstep: HBM idles while both select and the
+  // SM's L2 port is contended while both update.  The second CTA of every SM (linear index >= late_from; clusters are
+  // never split) starts late, so its streaming phase covers its neighbour's select + update.
+  if (kp.late_ns != 0 && (blockIdx.y * gridDim.x) >= kp.late_from) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(500);
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    } while (t - t0 < kp.late_ns);
+  }
   stamp(kp, 0);
   // ---------------------------------------------------------------- phase A: moments + level-0 histogram
   const int mode = p.moments_mode;
@@ -619,6 +614,19 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
   kp.inv_cm1 = 1.0f / (float)(count - 1);  // count == 1 -> inf; 0 * inf = NaN like torch.var
   kp.inv_sqrt_alpha_t = 1.0f / p->ddim.sqrt_alpha_t;
   kp.timeline = nullptr;
+  kp.late_from = 0; kp.late_ns = 0;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e_s = getenv("DU_FUSED_SKEW_US");
+    const double skew_us = e_s ? atof(e_s) : 0.0;
+    const int64_t ctas = p->B * plan.cluster;
+    if (skew_us > 0.0 && ctas > sms) {
+      kp.late_from = (uint32_t)((sms / plan.cluster) * plan.cluster);
+      kp.late_ns = (uint32_t)(skew_us * 1000.0);
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const char* tl_path = getenv("DU_FUSED_TIMELINE");  // debug only: synchronises and writes the per-CTA phase stamps
   const size_t tl_words = (size_t)p->B * plan.cluster * 8;

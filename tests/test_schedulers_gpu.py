@@ -33,8 +33,15 @@ def dev():
 
 
 def rel_close(a, b, rtol, atol=0.0):
+    """|a-b| <= rtol|b| + atol on the finite entries; NaN / +-inf must sit in exactly the same places (u = 0 gives
+    inf / NaN posterior scores in the reference)"""
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
-    return bool(((a - b).abs() <= rtol * b.abs() + atol).all())
+    fa, fb = torch.isfinite(a), torch.isfinite(b)
+    if not (torch.equal(fa, fb) and torch.equal(torch.isnan(a), torch.isnan(b))):
+        return False
+    if not torch.equal(a[~fa & ~torch.isnan(a)], b[~fb & ~torch.isnan(b)]):
+        return False
+    return bool(((a[fa] - b[fb]).abs() <= rtol * b[fb].abs() + atol).all())
 
 
 def build(case):
@@ -43,8 +50,8 @@ def build(case):
     mod = importlib.import_module(SU + MODULE_OF[variant])
     model = ToyADM(3, seed=seed, dropout=dropout).eval().to(dev())
     sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
-        dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True,
-             set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", timestep_spacing="leading", **cfg),
+        {**dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True,
+                set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", timestep_spacing="leading"), **cfg},
         unet=model, **kw)
     sched.set_timesteps(n_steps)
     return sched, model
@@ -259,5 +266,5 @@ def test_percentile_guidance_function_matches_reference(golden_dir, mode):
     got = out.detach().cpu()
     assert got.shape == want.shape
     # pixels whose variance sits on the percentile threshold may flip with a 1-ulp map difference
-    bad = (got - want).abs() > (2e-5 * want.abs() + 1e-6)
+    bad = ~(((got - want).abs() <= (2e-5 * want.abs() + 1e-6)) | (torch.isnan(got) & torch.isnan(want)) | (got == want))
     assert float(bad.float().mean()) < 0.002, f"{int(bad.sum())} of {bad.numel()} elements differ"
