@@ -48,6 +48,16 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` summary of this
+    round (profiles/ncu_traffic.json; written by tools/ncu_summary.py from the capture).  None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def algorithmic_bytes_per_element(M, score_bytes, sample_bytes=4):
     """(M+1)*s_in (scores + eps) + s_x (sample) + 4 (u -> map slot) + s_x (x_{t-1})."""
     return (M + 1) * score_bytes + sample_bytes + 4 + sample_bytes
@@ -201,8 +211,6 @@ def run_ours(args):
     eps, scores, sample = h_eps.to(dev), [s.to(dev) for s in h_scores], h_sample.to(dev)
     maps = torch.zeros(B, T_UC, C, H, W, device=dev, dtype=torch.float32)   # F8 accumulation buffer
 
-    ev_k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ev_k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     S_buf = torch.empty(C, H, W, device=dev, dtype=torch.float32)
     fused = (not args.unfused) and ops.fused_supported(C * H * W, dtype) > 0
     plan = None
@@ -211,24 +219,25 @@ def run_ours(args):
         plan = ops.FusedStep(scores, eps, sample, q, coeffs, sc["alpha_hat"], S=S_buf if args.batch_sum else None,
                              S_broadcast=bool(args.batch_sum), map_out=maps[:, 0])
     dominant = "fused_step_kernel" if fused else "moments_kernel"
+    prev_u = torch.empty(B, C, H, W, device=dev, dtype=torch.float32)
+    u_tmp = torch.empty(B, C, H, W, device=dev, dtype=torch.float32)
 
-    def step(i, timed=False):
+    def kernel_only(i):
+        """the dominant kernel alone (roofline.achieved is its algorithmic bytes / its average launch duration)"""
+        if fused:
+            plan.set_map_out(maps[:, i % T_UC])
+            plan.launch()
+        else:
+            ops.moments(scores, center=eps, mode="var_with_center", out=maps[:, i % T_UC])
+
+    def step(i):
         slot = maps[:, i % T_UC]
         if args.batch_sum:
             ops.batch_sum(eps, out=S_buf)            # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
         if fused:
             plan.set_map_out(slot)
-            if timed:
-                ev_k0[i].record()
-            r = plan.launch()
-            if timed:
-                ev_k1[i].record()
-            return r["prev"]
-        if timed:
-            ev_k0[i].record()
+            return plan.launch()["prev"]
         u = ops.moments(scores, center=eps, mode="var_with_center", out=slot)
-        if timed:
-            ev_k1[i].record()
         thr = ops.quantile_threshold(u, q)
         r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=S_buf if args.batch_sum else eps,
                             aux_broadcast=bool(args.batch_sum), post_M=float(M), inv_alpha_hat=1.0 / sc["alpha_hat"],
@@ -241,31 +250,61 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        step(i)
+        out = step(i)
     barrier()
+
+    # The K timed steps are captured into ONE CUDA graph (every C-ABI call is capturable: no host reads, no allocation),
+    # so the timed region holds exactly K steps of GPU work and no Python / launch latency between them.  The unfused
+    # chain allocates per call and is timed eagerly.
+    use_graph = fused and not args.eager
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(args.steps):
+                fn(i)
+        return g
+
     launches0 = ops.launch_count
+    if use_graph:
+        g_step, g_kernel = capture(step), capture(kernel_only)
+        n_step_launches = args.steps * (2 if args.batch_sum else 1)
+        g_step.replay(); g_kernel.replay()            # one untimed replay each
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
-        for i in range(args.steps):
-            out = step(i, timed=True)
+        if use_graph:
+            g_step.replay()
+        else:
+            launches0 = ops.launch_count
+            for i in range(args.steps):
+                out = step(i)
+            n_step_launches = ops.launch_count - launches0
         e1.record()
         barrier()
+        # the dominant kernel alone, K launches back to back on the same stream
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        if use_graph:
+            g_kernel.replay()
+        else:
+            for i in range(args.steps):
+                kernel_only(i)
+        k1.record()
+        barrier()
     ms = e0.elapsed_time(e1)
-    launches = ops.launch_count - launches0
-    k_ms = sum(a.elapsed_time(b) for a, b in zip(ev_k0, ev_k1)) / args.steps
-    k_bb_ms = None
-    if fused:   # cross-check of the per-launch figure: the same kernel launched back to back, two events around all K
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        b0.record()
-        for i in range(args.steps):
-            plan.set_map_out(maps[:, i % T_UC])
-            plan.launch()
-        b1.record()
-        torch.cuda.synchronize()
-        k_bb_ms = b0.elapsed_time(b1) / args.steps
+    launches = n_step_launches
+    k_ms = k0.elapsed_time(k1) / args.steps
+    # eager cross-check: the same K steps launched from Python (includes per-launch host latency)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for i in range(args.steps):
+        out = step(i)
+    b1.record()
+    torch.cuda.synchronize()
+    eager_ms = b0.elapsed_time(b1) / args.steps
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -273,25 +312,24 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    # ---- end to end through the public API with HOST buffers (pinned): H2D of the step's inputs and D2H of its results
+    # inside the timed region (diffusion_uncertainty_b200.host_step pipelines image chunks over three streams)
+    from diffusion_uncertainty_b200.host_step import HostStreamedUncertaintyStep
     h_prev = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
     h_map = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
+    host_step = HostStreamedUncertaintyStep(B, (C, H, W), M, dev, score_dtype=dtype, chunks=args.e2e_chunks)
 
     def e2e_step(i):
-        d_eps = h_eps.to(dev, non_blocking=True)
-        d_scores = [s.to(dev, non_blocking=True) for s in h_scores]
-        d_sample = h_sample.to(dev, non_blocking=True)
-        r = ops.uncertainty_step(d_scores, d_eps, d_sample, q, coeffs, sc["alpha_hat"], batch_sum=args.batch_sum,
-                                 map_out=maps[:, i % T_UC])
-        h_prev.copy_(r["prev"], non_blocking=True)
-        h_map.copy_(r["u"], non_blocking=True)
+        return host_step(h_scores, h_eps, h_sample, q, coeffs, sc["alpha_hat"], h_prev, h_map, batch_sum=bool(args.batch_sum),
+                         map_slot=maps[:, i % T_UC])
 
-    e2e_step(0)
+    e2e_step(0).synchronize()
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        e2e_step(i)
+        last = e2e_step(i)
+    last.synchronize()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -321,8 +359,11 @@ def run_ours(args):
             "step_hbm_frac": alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
             "step_algorithmic_GBps": alg_step / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": None,
-                         "kernel_ms": k_ms, "kernel_ms_back_to_back": k_bb_ms, "algorithmic_bytes": alg_kernel},
+                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": ncu_traffic(dominant),
+                         "kernel_ms": k_ms, "algorithmic_bytes": alg_kernel,
+                         "timing": "CUDA events around %d back-to-back launches%s" % (args.steps, " replayed from one CUDA graph" if use_graph else "")},
+            "ms_per_step_eager_python_loop": eager_ms,
+            "timed_region": "one CUDA graph of K steps" if use_graph else "K eager steps",
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s / e2e_steps * 1e3},
             "gpu_launches": launches,
@@ -347,6 +388,8 @@ def main():
     ap.add_argument("--batch-sum", type=int, default=1, help="1 = reference behaviour (posterior sum over the batch axis)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--unfused", action="store_true", help="time the 3-kernel chain instead of the single fused launch")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="image chunks of the host-buffer pipeline (e2e leg)")
+    ap.add_argument("--eager", action="store_true", help="time K eager launches from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

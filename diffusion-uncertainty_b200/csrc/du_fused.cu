@@ -221,59 +221,51 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
     }
     sync_all();  // candidate lists complete
     stamp(kp, 4);
-    if (crank == 0) {
-      uint32_t total = misc[6];
-      bool has_nan = misc[3] != 0;
-      for (unsigned r = 1; r < csize; ++r) {  // gather the peers' candidates behind the local ones
-        const uint32_t* pm = peer(misc, r);
-        const uint32_t* pw = peer(work, r);
-        const uint32_t cr = pm[6];
-        has_nan |= (pm[3] != 0);
-        for (uint32_t j = tid; j < cr; j += THREADS) work[total + j] = pw[j];
-        total += cr;
-      }
-      for (int j = tid; j < H0_BINS; j += THREADS) h0[j] = 0;  // reused: [0,1024) level 1, [1024,2048) level 2
-      __syncthreads();
-      for (uint32_t j = tid; j < total; j += THREADS) atomicAdd(&h0[(work[j] >> H2_BITS) & (H1_BINS - 1)], 1u);
-      __syncthreads();
-      locate_rank<H1_BINS, THREADS, false>(cluster, 1u, h0, kp.lo - below0, misc);
-      const uint32_t d1 = misc[0], below1 = misc[1];
-      __syncthreads();
-      const uint32_t prefix21 = want | (d1 << H2_BITS);
-      for (uint32_t j = tid; j < total; j += THREADS) {
-        const uint32_t key = work[j];
-        if ((key & ~(uint32_t)(H2_BINS - 1)) == prefix21) atomicAdd(&h0[H1_BINS + (key & (H2_BINS - 1))], 1u);
-      }
-      __syncthreads();
-      locate_rank<H2_BINS, THREADS, false>(cluster, 1u, h0 + H1_BINS, kp.lo - below0 - below1, misc);
-      const uint32_t key_lo = prefix21 | misc[0];
-      const uint32_t below = below0 + below1 + misc[1], bincount = misc[2];
-      __syncthreads();
-      const bool need_next = kp.hi >= below + bincount;  // the hi-th statistic is the smallest key above key_lo
-      if (need_next) {
-        uint32_t best = 0xffffffffu;
-        for (uint32_t j = tid; j < total; j += THREADS) { const uint32_t key = work[j]; if (key > key_lo && key < best) best = key; }
-        best = __reduce_min_sync(0xffffffffu, best);
-        if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
-        __syncthreads();
-      }
-      if (tid == 0) {
-        const uint32_t key_hi = need_next ? misc[4] : key_lo;
-        const bool rare = need_next && key_hi == 0xffffffffu && !has_nan;  // key_lo is the largest key of its level-0 bin
-        float t = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, kp.p.lerp_fma);
-        if (has_nan) t = __int_as_float(0x7fc00000);
-        for (unsigned r = 0; r < csize; ++r) {
-          uint32_t* pm = peer(misc, r);
-          pm[7] = __float_as_uint(t); pm[40] = rare ? 1u : 0u; pm[41] = key_lo;
-        }
-      }
+    // Every CTA gathers the cluster's candidates behind its own and finishes the select itself (identical lists give
+    // identical thresholds): no publish step, no third barrier.
+    uint32_t total = misc[6];
+    bool has_nan = misc[3] != 0;
+    for (unsigned i = 1; i < csize; ++i) {
+      const unsigned r = (crank + i) % csize;
+      const uint32_t* pm = peer(misc, r);
+      const uint32_t* pw = peer(work, r);
+      const uint32_t cr = pm[6];
+      has_nan |= (pm[3] != 0);
+      for (uint32_t j = tid; j < cr; j += THREADS) work[total + j] = pw[j];
+      total += cr;
     }
-    sync_all();  // threshold published
-    thr = __uint_as_float(misc[7]);
-    if (misc[40]) {  // rare: the successor of key_lo lives in a higher level-0 bin -> one pass for the smallest key above
-      const uint32_t key_lo = misc[41];
-      if (tid == 0) misc[4] = 0xffffffffu;
+    if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // peers' lists and flags are read
+    for (int j = tid; j < H0_BINS; j += THREADS) h0[j] = 0;  // reused: [0,1024) level 1, [1024,2048) level 2
+    __syncthreads();
+    for (uint32_t j = tid; j < total; j += THREADS) atomicAdd(&h0[(work[j] >> H2_BITS) & (H1_BINS - 1)], 1u);
+    __syncthreads();
+    locate_rank<H1_BINS, THREADS, false>(cluster, 1u, h0, kp.lo - below0, misc);
+    const uint32_t d1 = misc[0], below1 = misc[1];
+    __syncthreads();
+    const uint32_t prefix21 = want | (d1 << H2_BITS);
+    for (uint32_t j = tid; j < total; j += THREADS) {
+      const uint32_t key = work[j];
+      if ((key & ~(uint32_t)(H2_BINS - 1)) == prefix21) atomicAdd(&h0[H1_BINS + (key & (H2_BINS - 1))], 1u);
+    }
+    __syncthreads();
+    locate_rank<H2_BINS, THREADS, false>(cluster, 1u, h0 + H1_BINS, kp.lo - below0 - below1, misc);
+    const uint32_t key_lo = prefix21 | misc[0];
+    const uint32_t below = below0 + below1 + misc[1], bincount = misc[2];
+    __syncthreads();
+    const bool need_next = kp.hi >= below + bincount;  // the hi-th statistic is the smallest key above key_lo
+    uint32_t key_hi = key_lo;
+    if (need_next) {
+      uint32_t best = 0xffffffffu;
+      for (uint32_t j = tid; j < total; j += THREADS) { const uint32_t key = work[j]; if (key > key_lo && key < best) best = key; }
+      best = __reduce_min_sync(0xffffffffu, best);
+      if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
       __syncthreads();
+      key_hi = misc[4];
+    }
+    if (need_next && key_hi == 0xffffffffu && !has_nan) {
+      // rare: key_lo is the largest key of its level-0 bin -> the successor lives in a higher bin: one pass for the
+      // smallest key above key_lo, cluster-wide (the condition is identical in every CTA of the cluster)
+      if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
       uint32_t best = 0xffffffffu;
       for (int g = tid; g < ng4; g += THREADS) {
         const uint4 v = *reinterpret_cast<const uint4*>(u_s + 4 * g);
@@ -284,10 +276,12 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
       best = __reduce_min_sync(0xffffffffu, best);
       if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
       sync_all();
-      uint32_t key_hi = 0xffffffffu;
       for (unsigned r = 0; r < csize; ++r) key_hi = min(key_hi, peer(misc, r)[4]);
-      thr = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, kp.p.lerp_fma);
+      if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     }
+    thr = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, kp.p.lerp_fma);
+    if (has_nan) thr = __int_as_float(0x7fc00000);
+    return thr;   // one cluster-barrier arrival is pending; the kernel waits for it before it exits
   } else {
     // ---- general path: two more histogram levels over the whole slice
     uint32_t* h1 = work;
@@ -527,7 +521,14 @@ static bool fused_plan(int64_t n, int vec, FusedPlan* out) {
 template <typename T, int MT, int THREADS, int MINB>
 static int launch_fused_t(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
   auto kern = fused_step_kernel<T, MT, THREADS, MINB>;
-  DU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+  // per instantiation and device: raise the dynamic shared-memory limit once, not on every launch
+  static size_t smem_set[64] = {0};
+  int dev = 0;
+  DU_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || plan.smem > smem_set[dev]) {
+    DU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    if (dev >= 0 && dev < 64) smem_set[dev] = plan.smem;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)plan.cluster, (unsigned)kp.p.B, 1);
   cfg.blockDim = dim3((unsigned)THREADS);
@@ -615,12 +616,11 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
   kp.inv_sqrt_alpha_t = 1.0f / p->ddim.sqrt_alpha_t;
   kp.timeline = nullptr;
   kp.late_from = 0; kp.late_ns = 0;
-  {
+  if (const char* e_s = getenv("DU_FUSED_SKEW_US")) {  // experiment knob, off by default (measured: no gain)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* e_s = getenv("DU_FUSED_SKEW_US");
-    const double skew_us = e_s ? atof(e_s) : 0.0;
+    const double skew_us = atof(e_s);
     const int64_t ctas = p->B * plan.cluster;
     if (skew_us > 0.0 && ctas > sms) {
       kp.late_from = (uint32_t)((sms / plan.cluster) * plan.cluster);

@@ -397,7 +397,8 @@ class FusedStep:
                  coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
                  S: Optional[torch.Tensor] = None, S_broadcast: bool = False, higher: bool = True,
                  map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
-                 want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None):
+                 want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None,
+                 prev_out: Optional[torch.Tensor] = None):
         M = len(scores)
         if M < 1 or M > L.DU_MAX_M:
             raise ValueError(f"fused step: M={M} must be in [1, {L.DU_MAX_M}]")
@@ -436,8 +437,14 @@ class FusedStep:
         thr = torch.empty(r0.B, device=dev, dtype=torch.float32)
         P.thr_out = C.c_void_p(thr.data_ptr())
         res = {"u": None, "thr": thr, "x0": None, "eps": None, "mask": None}
-        res["prev"] = torch.empty(shape, device=dev, dtype=out_dtype)
-        P.prev_out, P.prev_stride, P.prev_dtype = C.c_void_p(res["prev"].data_ptr()), r0.n, _DT[out_dtype]
+        if prev_out is None:
+            prev_out = torch.empty(shape, device=dev, dtype=out_dtype)
+        pr = Rows(prev_out, "prev_out")
+        if pr.t is not prev_out or prev_out.dtype != out_dtype:
+            raise ValueError(f"fused step: prev_out must be a {out_dtype} tensor with contiguous rows")
+        _same_rows(r0, pr, "fused step(prev_out)")
+        res["prev"] = prev_out
+        P.prev_out, P.prev_stride, P.prev_dtype = pr.ptr, pr.stride, _DT[out_dtype]
         if want_x0:
             res["x0"] = torch.empty(shape, device=dev, dtype=out_dtype)
             P.x0_out, P.x0_stride = C.c_void_p(res["x0"].data_ptr()), r0.n
@@ -494,31 +501,38 @@ def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: 
                      coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
                      sum_source: Optional[torch.Tensor] = None, batch_sum: bool = True, higher: bool = True,
                      map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
-                     want_eps: bool = False, want_mask: bool = False, fused: Optional[bool] = None):
+                     want_eps: bool = False, want_mask: bool = False, fused: Optional[bool] = None,
+                     precomputed_sum: Optional[torch.Tensor] = None, prev_out: Optional[torch.Tensor] = None):
     """The percentile-guided posterior step, F1 -> F2a -> F5 -> F3 (+F8 when `map_out` is a slot of the
     accumulation buffer): PU/...posterior_distribution.py:153-162 + uncertainty_guidance.py:101-120 +
     SU/...zigzag_centered.py:472-510.  Returns dict(u, thr, prev, x0, eps, mask).
-    batch_sum=True reproduces the reference's `sum(dim=0)` over the batch axis (identity at B=1).
+    batch_sum=True reproduces the reference's `sum(dim=0)` over the batch axis (identity at B=1); `precomputed_sum` is that
+    row when the caller already has it (image chunks of a larger batch, or the all-reduced row under batch sharding).
     fused=None picks the single-launch cluster kernel whenever the shape/alignment allows it."""
     M = len(scores)
     for t in list(scores) + [eps, sample]:
         _require_cuda(t, "uncertainty_step input")
     src = eps if sum_source is None else sum_source
     S, bcast = (None if sum_source is None else src), False
-    if batch_sum and eps.shape[0] > 1:
+    if batch_sum and precomputed_sum is not None:
+        S, bcast = precomputed_sum, True
+    elif batch_sum and eps.shape[0] > 1:
         S, bcast = batch_sum_fn(src), True
     if fused is None:
         fused = _fused_eligible(scores, eps, sample, map_out, S)
     if fused:
         return fused_uncertainty_step(scores, eps, sample, q, coeffs, alpha_hat_t, moments_mode=moments_mode, S=S,
                                       S_broadcast=bcast, higher=higher, map_out=map_out, lerp_fma=lerp_fma, want_x0=want_x0,
-                                      want_eps=want_eps, want_mask=want_mask)
+                                      want_eps=want_eps, want_mask=want_mask, prev_out=prev_out)
     u = moments(scores, center=eps, mode=moments_mode, out=map_out)
     thr = quantile_threshold(u, q, lerp_fma=lerp_fma)
     r = guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=src if S is None else S, aux_broadcast=bcast,
                     higher=higher, post_M=float(M), inv_alpha_hat=float(1.0 / alpha_hat_t), want_prev=True, want_x0=want_x0,
                     want_eps=want_eps, want_mask=want_mask)
     r["u"], r["thr"] = u, thr
+    if prev_out is not None:
+        prev_out.copy_(r["prev"])
+        r["prev"] = prev_out
     return r
 
 

@@ -204,3 +204,25 @@ def test_fused_unsupported_falls_back_to_unfused_kernels(ops):
     r = ops.uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), 0.9, k, 0.5, batch_sum=False, want_mask=True)
     u2, mask2, _, prev2, _ = O.uncertainty_step_posterior(scores, eps, sample, 0.9, 3, torch.tensor(0.5), c, batch_sum=False)
     assert_close_rel(r["u"], u2, 1e-5)
+
+
+@pytest.mark.parametrize("batch_sum", [True, False])
+def test_host_streamed_step_matches_the_device_step(ops, batch_sum):
+    """host_step.HostStreamedUncertaintyStep (pinned host buffers, image chunks pipelined over three streams) gives the same
+    bits as one ops.uncertainty_step call on the whole batch"""
+    from diffusion_uncertainty_b200.host_step import HostStreamedUncertaintyStep
+    d = dev()
+    B, C, H, M = 13, 3, 32, 5
+    eps, scores, sample = synth(B, C, H, M, seed=17)
+    c, k = coeffs_for(ops, 180, 160)
+    a_hat = float(torch.cumprod(1 - O.make_betas(), 0)[180])
+    want = ops.uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), 0.9, k, a_hat, batch_sum=batch_sum)
+    hs = HostStreamedUncertaintyStep(B, (C, H, H), M, d, chunks=4)
+    h_prev = torch.empty(B, C, H, H).pin_memory()
+    h_map = torch.empty(B, C, H, H).pin_memory()
+    buf = torch.zeros(B, 2, C, H, H, device=d)
+    for _ in range(2):   # staging buffers are reused across calls
+        hs([s.pin_memory() for s in scores], eps.pin_memory(), sample.pin_memory(), 0.9, k, a_hat, h_prev, h_map,
+           batch_sum=batch_sum, map_slot=buf[:, 1]).synchronize()
+    assert bits_equal(h_map, want["u"]) and bits_equal(buf[:, 1], want["u"]) and bits_equal(h_prev, want["prev"])
+    assert float(buf[:, 0].abs().max()) == 0.0
