@@ -6,7 +6,7 @@ timeout 900 python -m pytest ${3:-tests/test_fused_gpu.py tests/test_ops_gpu.py}
 tail -6 gpurun_out/pytest_quick.log
 for cfg in ${1:-"1:1024 2:512"}; do
   c=${cfg%%:*}; t=${cfg##*:}
-  r=$(DU_FUSED_CLUSTER=$c DU_FUSED_THREADS=$t timeout 120 python bench.py --steps 30 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['kernel_ms'], d['roofline']['kernel_ms_back_to_back'], round(d['roofline']['frac'],4), d['ms_per_step'])" 2>&1 | tail -1)
+  r=$(DU_FUSED_CLUSTER=$c DU_FUSED_THREADS=$t timeout 120 python bench.py --steps 30 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['kernel_ms'], round(d['roofline']['frac'],4), d['ms_per_step'])" 2>&1 | tail -1)
   echo "cluster=$c threads=$t -> $r"
 done | tee gpurun_out/sweep2.txt
 timeout 120 python bench.py --steps 30 --warmup 3 --no-cpu --unfused 2>&1 | tail -1 > gpurun_out/bench_unfused.json
