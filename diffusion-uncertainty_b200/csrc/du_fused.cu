@@ -32,12 +32,18 @@ namespace cg = cooperative_groups;
 
 namespace du {
 
-constexpr int H0_BITS = 11, H1_BITS = 10, H2_BITS = 10;  // 31 value bits (sign is always 0)
+constexpr int H0_BITS = 12, H1_BITS = 10, H2_BITS = 9;  // 31 value bits (sign is always 0)
 constexpr int H0_BINS = 1 << H0_BITS, H1_BINS = 1 << H1_BITS, H2_BINS = 1 << H2_BITS;
-constexpr int CAND_CAP = H1_BINS + H2_BINS;  // candidate list (keys of the selected level-0 bin) overlays the level-1/2 histograms
-constexpr int HIST_WORDS = H0_BINS + H1_BINS + H2_BINS;
+// Level 0 is counted per CTA in 16-bit halves of 32-bit words (a CTA slice that fits shared memory has < 65536 elements),
+// so 4096 bins take the 8 KB that 2048 32-bit bins would.
+constexpr int H0_WORDS = H0_BINS / 2;
+// work area behind the level-0 histogram: [0, LIST_CAP) candidate keys of the selected level-0 bin, [LIST_CAP, +H1_BINS) their
+// level-1 histogram.  The general path (heavy ties) reuses the area as level-1 / level-2 histograms of the whole slice.
+constexpr int LIST_CAP = 1024;
+constexpr int WORK_WORDS = LIST_CAP + H1_BINS;
+constexpr int HIST_WORDS = H0_WORDS + WORK_WORDS;
 // misc words: [0..2] locate result, [3] nan flag, [4] min larger key, [5] next bin, [6] candidate count, [7] threshold,
-// [8..39] warp sums, [40] "successor not among the candidates" flag, [41] key_lo
+// [8..39] warp sums, [40] tiny-list count, [42] tensor-memory base
 constexpr int MISC_WORDS = 48;
 constexpr int MAX_CLUSTER = 8;
 
@@ -86,10 +92,12 @@ __device__ __forceinline__ void moments_group(const du_fused_params& p, int64_t 
 // ---- phase B: block-wide search of rank k in the histogram summed over the cluster's CTAs ----------------------------
 // hist_local points at this CTA's histogram for the level; peers are reached through DSMEM.  Result in misc[0..2]
 // (bin, count below the bin, count in the bin); for LAST also misc[5] = next non-empty bin above (or NBINS).
-template <int NBINS, int THREADS, bool LAST>
+// PACKED16: two 16-bit counters per word (bin 2i in the low half).
+template <int NBINS, int THREADS, bool LAST, bool PACKED16>
 __device__ __forceinline__ void locate_rank(cg::cluster_group& cluster, unsigned csize, uint32_t* hist_local, uint32_t k,
                                             uint32_t* misc) {
   constexpr int PER = (NBINS + THREADS - 1) / THREADS;
+  static_assert(!PACKED16 || PER % 2 == 0, "packed histograms need an even number of bins per thread");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t c[PER], tot = 0;
   const int first = tid * PER;
@@ -98,7 +106,26 @@ __device__ __forceinline__ void locate_rank(cg::cluster_group& cluster, unsigned
   if (first < NBINS) {
     for (unsigned r = 0; r < csize; ++r) {
       const uint32_t* h = (csize > 1) ? cluster.map_shared_rank(hist_local, r) : hist_local;
-      if constexpr (PER % 4 == 0) {   // one 16-byte (DSMEM) load per 4 bins
+      if constexpr (PACKED16) {
+        constexpr int W = PER / 2;
+        if constexpr (W % 4 == 0) {
+#pragma unroll
+          for (int j = 0; j < W; j += 4) {
+            const uint4 q = *reinterpret_cast<const uint4*>(h + first / 2 + j);
+            c[2 * j] += q.x & 0xffffu; c[2 * j + 1] += q.x >> 16; c[2 * j + 2] += q.y & 0xffffu; c[2 * j + 3] += q.y >> 16;
+            c[2 * j + 4] += q.z & 0xffffu; c[2 * j + 5] += q.z >> 16; c[2 * j + 6] += q.w & 0xffffu; c[2 * j + 7] += q.w >> 16;
+          }
+        } else if constexpr (W % 2 == 0) {
+#pragma unroll
+          for (int j = 0; j < W; j += 2) {
+            const uint2 q = *reinterpret_cast<const uint2*>(h + first / 2 + j);
+            c[2 * j] += q.x & 0xffffu; c[2 * j + 1] += q.x >> 16; c[2 * j + 2] += q.y & 0xffffu; c[2 * j + 3] += q.y >> 16;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < W; ++j) { const uint32_t q = h[first / 2 + j]; c[2 * j] += q & 0xffffu; c[2 * j + 1] += q >> 16; }
+        }
+      } else if constexpr (PER % 4 == 0) {   // one 16-byte (DSMEM) load per 4 bins
 #pragma unroll
         for (int j = 0; j < PER; j += 4) {
           const uint4 q = *reinterpret_cast<const uint4*>(h + first + j);
@@ -128,8 +155,14 @@ __device__ __forceinline__ void locate_rank(cg::cluster_group& cluster, unsigned
   if (lane == 31) wsum[warp] = incl;
   if (LAST && tid == 0) misc[5] = NBINS;
   __syncthreads();
-  uint32_t wprefix = 0;
-  for (int wI = 0; wI < warp; ++wI) wprefix += wsum[wI];
+  // exclusive prefix over the warp totals: lane l reads warp l's total, one shuffle scan per warp
+  uint32_t wtot = (lane < THREADS / 32) ? wsum[lane] : 0u, wincl = wtot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
+    if (lane >= o) wincl += t;
+  }
+  const uint32_t wprefix = __shfl_sync(0xffffffffu, wincl - wtot, warp);
   const uint32_t excl = wprefix + incl - tot;
   if (k >= excl && k < excl + tot) {
     uint32_t cum = excl;
@@ -212,15 +245,17 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 }
 
 // ---- phase B: the per-image threshold ------------------------------------------------------------------------------------
-// Level 0 (top 11 value bits) was histogrammed on the fly in phase A.  Fast path: the elements of the selected level-0
-// bin (typically ~2 % of the image) are compacted into a candidate list in ONE pass over the shared-memory map, CTA 0
-// gathers the cluster's lists through DSMEM and finishes the exact select on the list alone (two 10-bit levels, a few
-// elements per thread), then publishes the threshold to its peers.  Heavy ties (more than CAND_CAP elements in the bin)
-// take the general path: two more full histogram passes with one cluster barrier each.
+// Level 0 (top 12 value bits) was histogrammed on the fly in phase A.  Fast path: ONE pass over the shared-memory map
+// compacts the keys of the selected level-0 bin (typically ~1 % of the image) into a per-CTA candidate list and histograms
+// their next 10 bits; after one cluster barrier every CTA locates the level-1 bin in the summed histograms, picks the
+// handful of candidates that share the 22-bit prefix out of the cluster's lists (DSMEM reads, no copy) and warp 0 finishes
+// the exact select on those few keys.  Every CTA computes the same threshold from the same data: no publish step.
+// Heavy ties (more than LIST_CAP elements in the level-0 bin) take the general path: two more full histogram passes with
+// one cluster barrier each.
 template <int THREADS>
 __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, unsigned csize, unsigned crank, const FusedKParams& kp,
                                                   const float* u_s, uint32_t* h0, uint32_t* work, uint32_t* misc) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int ng4 = (int)(kp.L / 4);
   constexpr int LOW = H1_BITS + H2_BITS;
   auto sync_all = [&]() { if (csize > 1) cluster_barrier(); else __syncthreads(); };
@@ -228,24 +263,23 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
 
   sync_all();  // level-0 histograms of every CTA are complete
   stamp(kp, 2);
-  locate_rank<H0_BINS, THREADS, false>(cluster, csize, h0, kp.lo, misc);
+  locate_rank<H0_BINS, THREADS, false, true>(cluster, csize, h0, kp.lo, misc);
   const uint32_t d0 = misc[0], below0 = misc[1], cnt0 = misc[2];
   __syncthreads();
   stamp(kp, 3);
   const uint32_t want = d0 << LOW, msk0 = (uint32_t)(H0_BINS - 1) << LOW;
   float thr;
 
-  if (cnt0 <= (uint32_t)CAND_CAP) {
-    // ---- compaction without atomics.  The pass is issue-bound (8 warps per scheduler, every element examined), so the
-    // common case is kept to ~3 instructions per element: a trip only records ONE bit, "some of my 4 elements are in
-    // the selected bin" (xor/and per element, min3 tree, one compare).  The few flagged trips (about one per thread) are
-    // re-read afterwards, a block-wide exclusive scan of the per-thread counts assigns list slots, no atomics.
+  if (cnt0 <= (uint32_t)LIST_CAP) {
+    uint32_t* list = work;
+    uint32_t* h1 = work + LIST_CAP;   // zeroed at kernel start
     {
-      const int lane = tid & 31, warp = tid >> 5;
+      // ---- compaction.  The pass is issue-bound (every element examined), so the common case is kept to ~3 instructions
+      // per element: a trip only records ONE bit, "some of my 4 elements are in the selected bin".  The few flagged trips
+      // (about one per thread) are re-read afterwards; list slots come from one shared-memory atomic per warp (the order of
+      // the list does not matter).
       const int trips = (ng4 + THREADS - 1) / THREADS;
       const uint32_t* ub = reinterpret_cast<const uint32_t*>(u_s);
-      uint32_t* wsum = misc + 8;
-      uint32_t running = 0;  // candidates placed by earlier rounds (identical in every thread)
       for (int it0 = 0; it0 < trips; it0 += 32) {
         uint32_t flagged = 0;
         const int nj = min(32, trips - it0);
@@ -258,8 +292,8 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
             flagged |= (min(min(t0, t1), min(t2, t3)) == 0u ? 1u : 0u) << j;
           }
         }
-        // exact count of this thread's candidates (flagged trips only)
-        uint32_t cnt = 0;
+        if (!__any_sync(0xffffffffu, flagged != 0u)) continue;
+        uint32_t cnt = 0;   // exact count of this thread's candidates (flagged trips only)
         for (uint32_t f = flagged; f; f &= f - 1) {
           const int g = (it0 + __ffs((int)f) - 1) * THREADS + tid;
           const uint4 v = *reinterpret_cast<const uint4*>(ub + 4 * g);
@@ -271,77 +305,96 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
           const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
           if (lane >= o) incl += t;
         }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        // exclusive prefix over the warp totals: lane l reads warp l's total, one shuffle scan per warp
-        uint32_t wtot = (lane < THREADS / 32) ? wsum[lane] : 0u, wincl = wtot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
-          if (lane >= o) wincl += t;
-        }
-        const uint32_t round_total = __shfl_sync(0xffffffffu, wincl, 31);
-        const uint32_t wbase = __shfl_sync(0xffffffffu, wincl - wtot, warp);
-        uint32_t slot = running + wbase + incl - cnt;
+        const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t wbase = 0;
+        if (lane == 0) wbase = atomicAdd(&misc[6], wtotal);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        uint32_t slot = wbase + incl - cnt;   // < cnt0 <= LIST_CAP: the bin holds cnt0 elements cluster-wide
         for (uint32_t f = flagged; f; f &= f - 1) {
           const int g = (it0 + __ffs((int)f) - 1) * THREADS + tid;
           const uint4 v = *reinterpret_cast<const uint4*>(ub + 4 * g);
-          if ((v.x & msk0) == want) work[slot++] = v.x & 0x7fffffffu;
-          if ((v.y & msk0) == want) work[slot++] = v.y & 0x7fffffffu;
-          if ((v.z & msk0) == want) work[slot++] = v.z & 0x7fffffffu;
-          if ((v.w & msk0) == want) work[slot++] = v.w & 0x7fffffffu;
+          const uint32_t kk[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if ((kk[e] & msk0) == want) {
+              list[slot++] = kk[e];
+              atomicAdd(&h1[(kk[e] >> H2_BITS) & (H1_BINS - 1)], 1u);
+            }
+          }
         }
-        running += round_total;
-        __syncthreads();  // wsum is reused by the next round and by locate_rank
       }
-      if (tid == 0) misc[6] = running;
     }
-    sync_all();  // candidate lists complete
+    sync_all();  // candidate lists and their level-1 histograms are complete
     stamp(kp, 4);
-    // Every CTA gathers the cluster's candidates behind its own and finishes the select itself (identical lists give
-    // identical thresholds): no publish step, no third barrier.
-    uint32_t total = misc[6];
-    bool has_nan = misc[3] != 0;
-    for (unsigned i = 1; i < csize; ++i) {
-      const unsigned r = (crank + i) % csize;
-      const uint32_t* pm = peer(misc, r);
-      const uint32_t* pw = peer(work, r);
-      const uint32_t cr = pm[6];
-      has_nan |= (pm[3] != 0);
-      for (uint32_t j = tid; j < cr; j += THREADS) work[total + j] = pw[j];
-      total += cr;
-    }
-    if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // peers' lists and flags are read
-    for (int j = tid; j < H0_BINS; j += THREADS) h0[j] = 0;  // reused: [0,1024) level 1, [1024,2048) level 2
-    __syncthreads();
-    for (uint32_t j = tid; j < total; j += THREADS) atomicAdd(&h0[(work[j] >> H2_BITS) & (H1_BINS - 1)], 1u);
-    __syncthreads();
-    locate_rank<H1_BINS, THREADS, false>(cluster, 1u, h0, kp.lo - below0, misc);
-    const uint32_t d1 = misc[0], below1 = misc[1];
-    __syncthreads();
-    const uint32_t prefix21 = want | (d1 << H2_BITS);
-    for (uint32_t j = tid; j < total; j += THREADS) {
-      const uint32_t key = work[j];
-      if ((key & ~(uint32_t)(H2_BINS - 1)) == prefix21) atomicAdd(&h0[H1_BINS + (key & (H2_BINS - 1))], 1u);
-    }
-    __syncthreads();
-    locate_rank<H2_BINS, THREADS, false>(cluster, 1u, h0 + H1_BINS, kp.lo - below0 - below1, misc);
-    const uint32_t key_lo = prefix21 | misc[0];
-    const uint32_t below = below0 + below1 + misc[1], bincount = misc[2];
-    __syncthreads();
-    const bool need_next = kp.hi >= below + bincount;  // the hi-th statistic is the smallest key above key_lo
-    uint32_t key_hi = key_lo;
-    if (need_next) {
+    locate_rank<H1_BINS, THREADS, true, false>(cluster, csize, h1, kp.lo - below0, misc);
+    const uint32_t d1 = misc[0], below1 = misc[1], cnt1 = misc[2], next1 = misc[5];
+    const uint32_t prefix = want | (d1 << H2_BITS);            // 22 known bits of key_lo
+    const uint32_t k2 = kp.lo - below0 - below1;               // rank of key_lo among the cnt1 keys with that prefix
+    const bool need_next = kp.hi > kp.lo;                      // the upper statistic is the next key in sorted order
+    // ---- pick the keys with the prefix (and, if the successor lives in the next non-empty level-1 bin, the smallest key
+    // there) out of the cluster's lists.  h0 is free now: the tiny list goes to its first words.
+    uint32_t* tiny = h0;
+    bool has_nan = false;
+    {
+      const uint32_t next_prefix = want | (next1 << H2_BITS);
+      const bool want_next_bin = need_next && (k2 + 1 >= cnt1) && next1 < (uint32_t)H1_BINS;
       uint32_t best = 0xffffffffu;
-      for (uint32_t j = tid; j < total; j += THREADS) { const uint32_t key = work[j]; if (key > key_lo && key < best) best = key; }
-      best = __reduce_min_sync(0xffffffffu, best);
-      if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
-      __syncthreads();
-      key_hi = misc[4];
+      for (unsigned i = 0; i < csize; ++i) {
+        const unsigned r = (crank + i) % csize;
+        const uint32_t* pm = peer(misc, r);
+        const uint32_t* pl = peer(list, r);
+        const uint32_t cr = pm[6];
+        has_nan |= (pm[3] != 0);
+        for (uint32_t j = tid; j < cr; j += THREADS) {
+          const uint32_t key = pl[j];
+          const uint32_t hi22 = key & ~(uint32_t)(H2_BINS - 1);
+          if (hi22 == prefix) tiny[atomicAdd(&misc[40], 1u)] = key;
+          else if (want_next_bin && hi22 == next_prefix) best = min(best, key);
+        }
+      }
+      if (want_next_bin) {
+        best = __reduce_min_sync(0xffffffffu, best);
+        if (lane == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
+      }
     }
+    if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // peers' lists, histograms and flags are read
+    __syncthreads();
+    if (tid < 32) {
+      // warp 0: k2-th smallest of the cnt1 keys in `tiny`.  They share 22 bits: bitwise search over the low 9.
+      const uint32_t m = misc[40];   // == cnt1
+      uint32_t ans = 0;
+#pragma unroll 1
+      for (int b = H2_BITS - 1; b >= 0; --b) {
+        const uint32_t trial = prefix | ans | (1u << b);
+        uint32_t c = 0;
+        for (uint32_t j = lane; j < m; j += 32) c += (tiny[j] < trial);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c <= k2) ans |= (1u << b);
+      }
+      const uint32_t key_lo = prefix | ans;
+      uint32_t key_hi = key_lo;
+      if (need_next) {
+        // successor: a tie, else the smallest larger key with the same prefix, else the smallest key of the next level-1 bin
+        uint32_t le = 0, above = 0xffffffffu;
+        for (uint32_t j = lane; j < m; j += 32) {
+          const uint32_t key = tiny[j];
+          le += (key <= key_lo);
+          if (key > key_lo) above = min(above, key);
+        }
+        le = __reduce_add_sync(0xffffffffu, le);
+        above = __reduce_min_sync(0xffffffffu, above);
+        if (k2 + 1 < le) key_hi = key_lo;
+        else if (above != 0xffffffffu) key_hi = above;
+        else key_hi = misc[4];   // 0xffffffff: the successor lives in a higher level-0 bin (rare path below)
+      }
+      if (lane == 0) { misc[41] = key_lo; misc[43] = key_hi; }
+    }
+    __syncthreads();
+    const uint32_t key_lo = misc[41];
+    uint32_t key_hi = misc[43];
     if (need_next && key_hi == 0xffffffffu && !has_nan) {
-      // rare: key_lo is the largest key of its level-0 bin -> the successor lives in a higher bin: one pass for the
-      // smallest key above key_lo, cluster-wide (the condition is identical in every CTA of the cluster)
+      // rare: key_lo is the largest key of its level-0 bin -> one pass for the smallest key above key_lo, cluster-wide
+      // (the condition is identical in every CTA of the cluster: all of them read the same lists)
       if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
       uint32_t best = 0xffffffffu;
       for (int g = tid; g < ng4; g += THREADS) {
@@ -351,7 +404,7 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
         for (int e = 0; e < 4; ++e) best = min(best, (kk[e] > key_lo) ? kk[e] : 0xffffffffu);
       }
       best = __reduce_min_sync(0xffffffffu, best);
-      if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
+      if (lane == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
       sync_all();
       for (unsigned r = 0; r < csize; ++r) key_hi = min(key_hi, peer(misc, r)[4]);
       if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
@@ -376,7 +429,7 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
       }
     }
     sync_all();
-    locate_rank<H1_BINS, THREADS, false>(cluster, csize, h1, k_rank, misc);
+    locate_rank<H1_BINS, THREADS, false, false>(cluster, csize, h1, k_rank, misc);
     const uint32_t d1 = misc[0];
     k_rank -= misc[1];
     below += misc[1];
@@ -401,7 +454,7 @@ __device__ __forceinline__ float select_threshold(cg::cluster_group& cluster, un
       if ((tid & 31) == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
     }
     sync_all();
-    locate_rank<H2_BINS, THREADS, true>(cluster, csize, h2, k_rank, misc);
+    locate_rank<H2_BINS, THREADS, true, false>(cluster, csize, h2, k_rank, misc);
     const uint32_t key_lo = prefix21 | misc[0];
     below += misc[1];
     const uint32_t bincount = misc[2];
@@ -509,11 +562,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_step_kernel(const __grid_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* u_s = reinterpret_cast<float*>(smem_raw);
   uint32_t* h0 = reinterpret_cast<uint32_t*>(u_s + L);
-  uint32_t* h1 = h0 + H0_BINS;              // candidate list, or the level-1 / level-2 histograms on the general path
-  uint32_t* misc = h1 + CAND_CAP;
+  uint32_t* h1 = h0 + H0_WORDS;             // work area: candidate list + level-1 histogram (or levels 1 / 2 on the general path)
+  uint32_t* misc = h1 + WORK_WORDS;
 
   const bool use_tmem = kp.tmem_cols != 0;
-  if (use_tmem && tid < 32) tmem_alloc(&misc[42], kp.tmem_cols);
+  // A kernel that contains tcgen05.alloc keeps a second CTA off the SM until the first one has given up its allocation
+  // permit, so warp 0 relinquishes it on every path (measured: without it the non-stash launches ran one CTA per SM).
+  if (tid < 32) {
+    if (use_tmem) tmem_alloc(&misc[42], kp.tmem_cols);
+    else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   for (int j = tid; j < HIST_WORDS; j += THREADS) h0[j] = 0;
   if (tid < MISC_WORDS && tid != 42) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
   if (use_tmem) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -552,7 +610,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_step_kernel(const __grid_
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       nan_seen |= (u[e] != u[e]);
-      atomicAdd(&h0[(__float_as_uint(u[e]) >> (H1_BITS + H2_BITS)) & (H0_BINS - 1)], 1u);
+      const uint32_t bin = __float_as_uint(u[e]) >> (H1_BITS + H2_BITS);   // sign bit is 0: 12 bits
+      atomicAdd(&h0[bin >> 1], (bin & 1u) ? 0x10000u : 1u);
     }
 #pragma unroll
     for (int h = 0; h < VEC / 4; ++h) {
@@ -631,15 +690,31 @@ static bool fused_plan(int64_t n, int vec, int64_t B, FusedPlan* out) {
 }
 
 template <typename T, int MT, int THREADS, int MINB>
-static int launch_fused_t(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
+static int launch_fused_t(const FusedKParams& kp_in, const FusedPlan& plan, cudaStream_t st) {
   auto kern = fused_step_kernel<T, MT, THREADS, MINB>;
   // per instantiation and device: raise the dynamic shared-memory limit once, not on every launch
   static size_t smem_set[64] = {0};
+  static int occ_cache[64] = {0};
+  static size_t occ_smem[64] = {0};
   int dev = 0;
   DU_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || plan.smem > smem_set[dev]) {
     DU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     if (dev >= 0 && dev < 64) smem_set[dev] = plan.smem;
+  }
+  FusedKParams kp = kp_in;
+  if (kp.tmem_cols != 0) {
+    // The eps stash asks for tmem_cols tensor-memory columns per CTA.  tcgen05.alloc BLOCKS while the SM's 512 columns are
+    // taken, and a blocked CTA whose cluster peers wait at a barrier could deadlock against another cluster, so the stash
+    // is only used when every CTA that can be co-resident on an SM (the occupancy the runtime reports for this
+    // instantiation and shared-memory size) gets its columns at once.
+    int occ = 0;
+    if (dev >= 0 && dev < 64 && occ_cache[dev] != 0 && occ_smem[dev] == plan.smem) occ = occ_cache[dev];
+    else {
+      DU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, plan.smem));
+      if (dev >= 0 && dev < 64) { occ_cache[dev] = occ; occ_smem[dev] = plan.smem; }
+    }
+    if (occ < 1 || kp.tmem_cols * (uint32_t)occ > 512u) { kp.tmem_cols = 0; kp.tmem_cpg = 0; }
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)plan.cluster, (unsigned)kp.p.B, 1);
@@ -731,7 +806,8 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
   kp.tmem_cols = 0; kp.tmem_cpg = 0;
   {
     // eps stash in tensor memory: fp32 scores whose eps is read in phase A anyway, fp32 sample/outputs (the fast update),
-    // whole warps only, and the columns of all co-resident CTAs must fit the SM's 512
+    // whole warps only; whether the columns of all co-resident CTAs fit the SM's 512 is decided per instantiation in
+    // launch_fused_t
     const char* e_tm = getenv("DU_FUSED_TMEM");
     const int64_t ng = kp.L / 4;
     const bool fast_c = p->ddim.prediction_type == DU_PRED_EPSILON && !p->ddim.use_clipped_model_output &&
@@ -741,12 +817,7 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
       const uint32_t need = trips * 4u * (uint32_t)(plan.threads / 128);
       uint32_t cols = 32;
       while (cols < need) cols <<= 1;
-      const size_t per_cta_smem = plan.smem + 1024;
-      int resident = (int)((228 * 1024) / per_cta_smem);
-      resident = resident < 2048 / plan.threads ? resident : 2048 / plan.threads;
-      resident = resident < 65536 / (plan.threads * 64) ? resident : 65536 / (plan.threads * 64);
-      if (resident < 1) resident = 1;
-      if (need <= 512 && cols * (uint32_t)resident <= 512) { kp.tmem_cols = cols; kp.tmem_cpg = trips * 4u; }
+      if (need <= 512) { kp.tmem_cols = cols; kp.tmem_cpg = trips * 4u; }
     }
   }
   if (const char* e_s = getenv("DU_FUSED_SKEW_US")) {  // experiment knob, off by default (measured: no gain)
