@@ -97,6 +97,7 @@ PROTOTYPES = {
     "du_image_uint8": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, vp]),
     "du_fused_uncertainty_step": (C.c_int, [C.POINTER(FusedParams), vp]),
     "du_fused_supported": (C.c_int, [i64, C.c_int]),
+    "du_fused_last_kernel": (C.c_int, []),
 }
 
 _lib = None

@@ -387,6 +387,12 @@ def fused_supported(n: int, dtype: torch.dtype) -> int:
     return int(L.load().du_fused_supported(int(n), _DT[dtype]))
 
 
+def fused_last_kernel() -> str:
+    """Name of the kernel the last fused launch of this thread used ('fused_step_kernel': three-phase cluster kernel,
+    'fused_pred_kernel': predictive single-pass kernel; '' before the first launch)."""
+    return {0: "", 1: "fused_step_kernel", 2: "fused_pred_kernel"}[int(L.load().du_fused_last_kernel())]
+
+
 class FusedStep:
     """A prepared du_fused_uncertainty_step call: the parameter block is built once, `launch()` is a single
     C-ABI call (one kernel launch), so a sampling loop (or a CUDA-graph capture) pays no per-step Python

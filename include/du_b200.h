@@ -257,6 +257,10 @@ typedef struct du_fused_params {
 /* returns DU_ERR_TOO_LARGE when a row does not fit the cluster's shared memory (use the unfused calls) */
 int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t stream);
 int du_fused_supported(int64_t n, int score_dtype);
+/* Which kernel the calling thread's last du_fused_uncertainty_step launched: 0 = none yet, 1 = the three-phase cluster
+ * kernel (fused_step_kernel), 2 = the predictive single-pass kernel (fused_pred_kernel; slices of >= 4 trips with the
+ * epsilon-prediction fp32 update).  Both give bit-identical results; benchmarks use this to name what they timed. */
+int du_fused_last_kernel(void);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,110 @@ def test_fused_imagenet128_rows(ops):
     run_case(ops, 3, 3, 128, 5, 0.9, "var_with_center", batch_sum=True, higher=True, seed=11)
 
 
+# ---- the predictive single-pass kernel (du_fused_pred.cu) serves slices of >= 4 trips; the shapes below are eligible, the
+# 32x32 cases above run the three-phase kernel.  DU_FUSED_PRED=0 forces the three-phase kernel on the same shapes.
+@pytest.mark.parametrize("pred,threads", [(1, 384), (1, 512), (0, 0)])
+@pytest.mark.parametrize("mode,higher,batch_sum", [("var_with_center", True, True), ("centered", False, False), ("var", True, False)])
+def test_fused_predictive_kernel_matches_oracle(ops, monkeypatch, pred, threads, mode, higher, batch_sum):
+    env = {"DU_FUSED_PRED": pred}
+    if threads:
+        env["DU_FUSED_PRED_THREADS"] = threads
+    run_case(ops, 3, 3, 128, 5, 0.9, mode, batch_sum=batch_sum, higher=higher, seed=21, env=env, monkeypatch=monkeypatch)
+    run_case(ops, 5, 3, 64, 5, 0.9, mode, batch_sum=batch_sum, higher=higher, seed=22, env=env, monkeypatch=monkeypatch)
+
+
+@pytest.mark.parametrize("cluster,threads,pthreads", [(1, 1024, 768), (1, 1024, 1024), (2, 512, 384), (4, 512, 384)])
+def test_fused_predictive_kernel_cluster_shapes(ops, monkeypatch, cluster, threads, pthreads):
+    run_case(ops, 3, 3, 128, 5, 0.75, "var_with_center", batch_sum=True, higher=True, seed=30 + cluster,
+             env={"DU_FUSED_CLUSTER": cluster, "DU_FUSED_THREADS": threads, "DU_FUSED_PRED_THREADS": pthreads}, monkeypatch=monkeypatch)
+
+
+@pytest.mark.parametrize("q,higher", [(0.0, True), (1.0, True), (0.5, False), (0.999, True), (0.37, False), (0.02, True)])
+def test_fused_predictive_kernel_quantile_edges(ops, q, higher):
+    run_case(ops, 2, 3, 128, 4, q, "var_with_center", batch_sum=True, higher=higher, seed=8)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_fused_predictive_kernel_16bit_scores(ops, dtype):
+    run_case(ops, 2, 4, 128, 5, 0.9, "var_with_center", batch_sum=False, higher=True, dtype=dtype, seed=4)
+
+
+@pytest.mark.parametrize("sigma", [6.0, 0.5])
+def test_fused_predictive_kernel_band_miss_falls_back_exactly(ops, monkeypatch, sigma):
+    """An image whose pilot rows (every trips-th row of 32 groups) look nothing like the rest: the predicted band misses the
+    true order statistics, the kernel must notice (rank check against the FULL histogram) and redo the image exactly.
+    sigma = 0.5 shrinks the band so that plain random images miss it as well."""
+    monkeypatch.setenv("DU_FUSED_BAND_SIGMA", str(sigma))
+    d = dev()
+    B, C, H, M, q = 3, 3, 128, 5, 0.9
+    eps, scores, sample = synth(B, C, H, M, seed=17)
+    n = C * H * H
+    flat = [s.view(B, n) for s in scores]
+    e = eps.view(B, n)
+    # rows of 128 elements; make every 4th row nearly constant across the M samples (tiny variance): whatever the pilot
+    # stride is (16 with 384 threads, 12 with 512), a large part of the pilot sample is then unrepresentative
+    rows = torch.arange(n // 128)
+    sel = (rows % 4 == 0).repeat_interleave(128)
+    for f in flat:
+        f[:, sel] = e[:, sel] + 1e-4 * (f[:, sel] - e[:, sel])
+    c, k = coeffs_for(ops, 300, 280)
+    a_hat = torch.cumprod(1 - O.make_betas(), 0)[300]
+    res = ops.fused_uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), q, k, float(a_hat), want_mask=True,
+                                     want_eps=True, want_x0=True)
+    u_k = res["u"].cpu()
+    assert_close_rel(u_k, O.variance_with_center(scores, eps), 1e-5, atol=1e-12)
+    assert bits_equal(res["thr"], torch.quantile(u_k.flatten(1), q, dim=1))
+    mask_o = O.calculate_threshold_map(float(q), None, u_k, "higher")
+    assert bits_equal(res["mask"], mask_o)
+    eps_o = O.posterior_blend(eps, u_k, mask_o, M, a_hat, batch_sum=False)
+    prev_o, x0_o, _ = O.ddim_step(eps_o, sample, c)
+    assert close_same_nonfinite(res["eps"], eps_o) and close_same_nonfinite(res["x0"], x0_o) and close_same_nonfinite(res["prev"], prev_o)
+    # the launch without the optional outputs (another instantiation) gives the same x_{t-1}
+    res2 = ops.fused_uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), q, k, float(a_hat))
+    assert bits_equal(res2["prev"], res["prev"]) and bits_equal(res2["thr"], res["thr"])
+
+
+def test_fused_predictive_kernel_ties_and_nan(ops):
+    """quantised scores (massive ties, zero variances -> candidate-list overflow / heavy level-0 bins) and a NaN image at a
+    shape the predictive kernel serves"""
+    d = dev()
+    g = torch.Generator().manual_seed(5)
+    shp = (3, 3, 128, 128)
+    eps = (torch.randn(shp, generator=g) * 2).round() / 2
+    scores = [eps + (torch.randn(shp, generator=g)).round() * 0.5 for _ in range(4)]
+    scores[1][2, 0, 0, 0] = float("nan")
+    sample = torch.randn(shp, generator=g)
+    c, k = coeffs_for(ops, 300, 280)
+    a_hat = torch.cumprod(1 - O.make_betas(), 0)[300]
+    res = ops.fused_uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), 0.9, k, float(a_hat), want_mask=True,
+                                     want_eps=True)
+    u_k = res["u"].cpu()
+    thr_o = torch.quantile(u_k.flatten(1), 0.9, dim=1)
+    assert bits_equal(res["thr"], thr_o) and torch.isnan(thr_o[2])
+    mask_o = O.calculate_threshold_map(0.9, None, u_k, "higher")
+    assert bits_equal(res["mask"], mask_o) and mask_o[2].sum() == 0
+    eps_o = O.posterior_blend(eps, u_k, mask_o, 4, a_hat, batch_sum=False)
+    assert close_same_nonfinite(res["eps"], eps_o)
+
+
+def test_fused_predictive_kernel_equals_three_phase_kernel_bitwise(ops, monkeypatch):
+    """same arithmetic, different schedule: every output of the two kernels is bit-identical"""
+    d = dev()
+    eps, scores, sample = synth(4, 3, 128, 5, seed=12)
+    c, k = coeffs_for(ops, 180, 160)
+    a_hat = float(torch.cumprod(1 - O.make_betas(), 0)[180])
+    sg, eg, xg = [s.to(d) for s in scores], eps.to(d), sample.to(d)
+    S = eps.sum(0).to(d)
+    out = {}
+    for pred in (1, 0):
+        monkeypatch.setenv("DU_FUSED_PRED", str(pred))
+        r = ops.fused_uncertainty_step(sg, eg, xg, 0.9, k, a_hat, S=S, S_broadcast=True, want_mask=True, want_eps=True, want_x0=True)
+        torch.cuda.synchronize()
+        out[pred] = {kk: v.clone() for kk, v in r.items() if v is not None}
+    for kk in out[1]:
+        assert bits_equal(out[1][kk], out[0][kk]), kk
+
+
 @pytest.mark.parametrize("q,higher", [(0.0, True), (1.0, True), (0.5, False), (0.999, True), (0.37, False)])
 def test_fused_quantile_edges(ops, q, higher):
     run_case(ops, 3, 3, 32, 4, q, "var_with_center", batch_sum=True, higher=higher, seed=7)

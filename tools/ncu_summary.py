@@ -11,6 +11,7 @@ import sys
 
 rep, tag = sys.argv[1], sys.argv[2]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles")   # on the GPU box: gpurun_out/ (the only directory that travels back)
 
 
 def page(name):
@@ -24,7 +25,7 @@ keep = [h for h in hdr if any(h.startswith(p) for p in (
     "Kernel Name", "gpu__time_duration", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput", "sm__throughput",
     "lts__throughput", "l1tex__throughput", "launch__", "smsp__inst_executed.sum", "sm__warps_active", "smsp__issue_active",
     "smsp__average_warps_issue_stalled", "lts__t_sector_hit_rate", "sm__inst_executed_pipe", "l1tex__data_bank_conflicts"))]
-with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.csv"), "w", newline="") as f:
+with open(os.path.join(OUT, f"{tag}_ncu_full_summary.csv"), "w", newline="") as f:
     w = csv.writer(f)
     w.writerow(["metric", "unit"] + [f"launch{i}" for i in range(len(data))])
     for h in keep:
@@ -44,7 +45,7 @@ for d in data:
     traffic[kname] = {"dram_bytes_per_launch": val(d, "dram__bytes_read.sum") + val(d, "dram__bytes_write.sum"),
                       "dram_read": val(d, "dram__bytes_read.sum"), "dram_write": val(d, "dram__bytes_write.sum"),
                       "gpu_time_us_under_ncu": float(d[hdr.index("gpu__time_duration.sum")]), "report": os.path.basename(rep), "tag": tag}
-json.dump(traffic, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+json.dump(traffic, open(os.path.join(OUT, "ncu_traffic.json"), "w"), indent=1)
 
 # per-phase split of the SASS: segments delimited by barriers
 src = page("source")
@@ -63,6 +64,6 @@ for n, r in enumerate(body):
         if seg_s > tot_s * 0.003 or seg_i > tot_i * 0.003:
             lines.append(f"{n},{seg_s},{100 * seg_s / tot_s:.1f},{seg_i},{100 * seg_i / tot_i:.1f},{r[si].strip()[:40]}")
         seg_s = seg_i = 0
-open(os.path.join(ROOT, "profiles", f"{tag}_ncu_phase_split.csv"), "w").write("\n".join(lines) + "\n")
+open(os.path.join(OUT, f"{tag}_ncu_phase_split.csv"), "w").write("\n".join(lines) + "\n")
 print(json.dumps(traffic, indent=1))
 print("\n".join(lines[:40]))

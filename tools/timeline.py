@@ -13,11 +13,17 @@ for k, nm in enumerate(names):
         print(f"  {nm:16s} min {r.min():7.2f}  mean {r.mean():7.2f}  p90 {np.percentile(r, 90):7.2f}  max {r.max():7.2f}")
 if a.shape[1] > 7 and (a[:, 7] > 0).any():
     r = (a[:, 7][a[:, 7] > 0] - t0) / 1e3
-    print(f"  {'flag loop done':16s} min {r.min():7.2f}  mean {r.mean():7.2f}  p90 {np.percentile(r, 90):7.2f}  max {r.max():7.2f}")
-    ok = (a[:, 3] > 0) & (a[:, 7] > 0)
-    print(f"  {'locate0 done':>16s} -> {'flag loop done':16s} mean {((a[ok, 7] - a[ok, 3]) / 1e3).mean():7.2f}")
+    print(f"  {'locate1 done':16s} min {r.min():7.2f}  mean {r.mean():7.2f}  p90 {np.percentile(r, 90):7.2f}  max {r.max():7.2f}")
+    ok = (a[:, 4] > 0) & (a[:, 7] > 0)
+    print(f"  {'lists complete':>16s} -> {'locate1 done':16s} mean {((a[ok, 7] - a[ok, 4]) / 1e3).mean():7.2f}")
 d = np.diff(a[:, :7], axis=1) / 1e3
 for k in range(6):
     ok = (a[:, k] > 0) & (a[:, k + 1] > 0)
     if ok.any():
         print(f"  {names[k]:>16s} -> {names[k+1]:16s} mean {d[ok, k].mean():7.2f}  max {d[ok, k].max():7.2f}")
+
+# extra debug stamps (slots 8..15), relative to "lists complete"
+for k in range(8, a.shape[1]):
+    ok = (a[:, k] > 0) & (a[:, 4] > 0)
+    if ok.any():
+        print(f"  slot {k}: after lists complete mean {((a[ok, k] - a[ok, 4]) / 1e3).mean():7.2f}  max {((a[ok, k] - a[ok, 4]) / 1e3).max():7.2f}")
