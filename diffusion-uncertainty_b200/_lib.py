@@ -24,7 +24,7 @@ ZN_BELOW, ZN_ABOVE, ZN_MULTISCALE = range(3)
 # du_prediction_type
 PRED_EPSILON, PRED_SAMPLE, PRED_V = range(3)
 # du_guidance
-GUIDE_NONE, GUIDE_POSTERIOR, GUIDE_GRAD_BLEND, GUIDE_GRAD_ADD, GUIDE_WEIGHTS = range(5)
+GUIDE_NONE, GUIDE_POSTERIOR, GUIDE_GRAD_BLEND, GUIDE_GRAD_ADD, GUIDE_WEIGHTS, GUIDE_LINCOMB = range(6)
 
 i64, i32, f32, vp, sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
 
@@ -47,9 +47,10 @@ class GuidedParams(C.Structure):
         ("ddim", DdimCoeffs),
         ("B", i64), ("n", i64),
         ("prev_out", vp), ("prev_stride", i64), ("prev_dtype", i32), ("_pad0", i32),
-        ("x0_out", vp), ("x0_stride", i64), ("x0_dtype", i32), ("_pad1", i32),
+        ("x0_out", vp), ("x0_stride", i64), ("x0_dtype", i32), ("x0_unguided", i32),
         ("eps_out", vp), ("eps_out_stride", i64), ("eps_out_dtype", i32), ("_pad2", i32),
         ("mask_out", vp), ("mask_out_stride", i64),
+        ("mask_period", i64),
     ]
 
 
@@ -98,6 +99,13 @@ PROTOTYPES = {
     "du_fused_uncertainty_step": (C.c_int, [C.POINTER(FusedParams), vp]),
     "du_fused_supported": (C.c_int, [i64, C.c_int]),
     "du_fused_last_kernel": (C.c_int, []),
+    "du_flip_h": (C.c_int, [vp, i64, C.c_int, i64, i64, i64, i64, vp, i64, C.c_int, vp]),
+    "du_flip_sqdiff": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, i64, i64, i64, i64, C.c_int, vp, i64, vp]),
+    "du_moments_backward": (C.c_int, [C.POINTER(vp), C.c_int, i64, C.c_int, vp, i64, C.c_int, C.c_int, vp, i64, C.c_int, i64, i64,
+                                      C.POINTER(vp), i64, C.c_int, vp, i64, vp]),
+    "du_column_kth": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, vp, vp]),
+    "du_row_sum": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, vp]),
+    "du_slot_sum": (C.c_int, [vp, i64, i64, C.c_int, i64, C.c_int, i64, vp, i64, vp]),
 }
 
 _lib = None

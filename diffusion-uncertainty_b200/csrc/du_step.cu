@@ -5,42 +5,11 @@
 // (no FMA contraction) so fp32 results are bit-identical to the eager torch expressions.
 #include <cooperative_groups.h>
 
-#include "du_common.cuh"
+#include "du_rows.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace du {
-
-// Generic driver: functor f.template run<VEC>(b, i) handles VEC elements of row b starting at i.
-template <bool VECTOR, typename F>
-__global__ void __launch_bounds__(256) rows_kernel(int64_t B, int64_t n, const __grid_constant__ F f) {
-  constexpr int VEC = VECTOR ? 4 : 1;
-  const int64_t groups = (n + VEC - 1) / VEC;
-  for (int64_t b = blockIdx.y; b < B; b += gridDim.y)
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x)
-      f.template run<VEC>(b, g * VEC);
-}
-
-template <typename F>
-static int launch_rows(int64_t B, int64_t n, bool vec, const F& f, cudaStream_t st) {
-  if (B == 0 || n == 0) return DU_OK;
-  RowGrid g = row_grid(B, vec ? n / 4 : n, 256);
-  if (vec) rows_kernel<true, F><<<g.grid, g.block, 0, st>>>(B, n, f);
-  else rows_kernel<false, F><<<g.grid, g.block, 0, st>>>(B, n, f);
-  DU_LAUNCH_CHECK("rows_kernel");
-  return DU_OK;
-}
-
-template <int VEC>
-__device__ __forceinline__ void loadv(const void* base, int64_t idx, int dt, float (&v)[VEC]) {
-  if constexpr (VEC == 4) load4(base, idx, dt, v);
-  else v[0] = load1(base, idx, dt);
-}
-template <int VEC>
-__device__ __forceinline__ void storev(void* base, int64_t idx, int dt, const float (&v)[VEC]) {
-  if constexpr (VEC == 4) store4(base, idx, dt, v);
-  else store1(base, idx, dt, v[0]);
-}
 
 // ---- F2a/F2b masks ----------------------------------------------------------------------------------
 struct ThrMaskF {
@@ -145,6 +114,8 @@ __device__ __forceinline__ float guided_eps(int guidance, float eps, float m, fl
       return __fadd_rn(eps, __fmul_rn(__fmul_rn(lam, aux), m));
     case DU_GUIDE_WEIGHTS:
       return __fmul_rn(eps, m);
+    case DU_GUIDE_LINCOMB:   // a*eps + lam*g (a travels in post_M): SU/scheduling_ddim_mc_dropout_gradient.py:514
+      return __fadd_rn(__fmul_rn(post_M, eps), __fmul_rn(lam, aux));
     default:
       return eps;
   }
@@ -159,7 +130,8 @@ struct GuidedF {
     const bool need_u = (p.u != nullptr);
     if (need_u) loadv<VEC>(p.u, b * p.u_stride + i, DU_F32, uu);
     if (p.mask) {
-      loadv<VEC>(p.mask, b * p.mask_stride + i, DU_F32, m);
+      // mask_period: a [B,1,H,W] mask broadcast over the channels of a [B,C,H,W] row (flip_threshold, SU/scheduling_ddim_flip_threshold.py:541)
+      loadv<VEC>(p.mask, b * p.mask_stride + (p.mask_period > 0 ? i % p.mask_period : i), DU_F32, m);
     } else if (p.thr) {
       float tb = __ldg(p.thr + b);
 #pragma unroll
@@ -174,7 +146,7 @@ struct GuidedF {
       eg[e] = guided_eps(p.guidance, e0[e], m[e], need_u ? uu[e] : 0.0f, p.aux ? ax[e] : e0[e], p.lam, p.post_M,
                          p.inv_alpha_hat);
       if (!p.skip_ddim) {
-        if (p.guidance == DU_GUIDE_WEIGHTS) {
+        if (p.guidance == DU_GUIDE_WEIGHTS || p.x0_unguided) {
           // F4: x0 from the UNMASKED model output, direction from the masked one, noise not re-added
           du_ddim_coeffs c = p.ddim;
           c.add_noise = 0;
@@ -479,7 +451,7 @@ extern "C" int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_
 
 extern "C" int du_guided_step(const du_guided_params* p, du_stream_t stream) {
   if (!p) return set_error(DU_ERR_BAD_ARG, "du_guided_step: null params");
-  if (p->guidance < DU_GUIDE_NONE || p->guidance > DU_GUIDE_WEIGHTS) return set_error(DU_ERR_BAD_ARG, "du_guided_step: bad guidance %d", p->guidance);
+  if (p->guidance < DU_GUIDE_NONE || p->guidance > DU_GUIDE_LINCOMB) return set_error(DU_ERR_BAD_ARG, "du_guided_step: bad guidance %d", p->guidance);
   if (!check_view(p->eps, p->eps_dtype) || p->B < 0 || p->n < 0) return set_error(DU_ERR_BAD_ARG, "du_guided_step: bad eps view");
   if (!p->skip_ddim) {
     int rc = check_coeffs(&p->ddim, "du_guided_step");
@@ -488,16 +460,19 @@ extern "C" int du_guided_step(const du_guided_params* p, du_stream_t stream) {
     if (p->guidance == DU_GUIDE_WEIGHTS && p->ddim.prediction_type != DU_PRED_EPSILON)
       return set_error(DU_ERR_BAD_ARG, "du_guided_step: masked re-step is implemented only for prediction type epsilon");
   }
-  if (p->guidance != DU_GUIDE_NONE && !p->mask && !p->thr) return set_error(DU_ERR_BAD_ARG, "du_guided_step: guidance needs thr or mask");
+  if (p->guidance != DU_GUIDE_NONE && p->guidance != DU_GUIDE_GRAD_ADD && p->guidance != DU_GUIDE_LINCOMB && !p->mask && !p->thr)
+    return set_error(DU_ERR_BAD_ARG, "du_guided_step: guidance needs thr or mask");
+  if (p->mask_period < 0 || (p->mask_period > 0 && (!p->mask || p->n % p->mask_period != 0)))
+    return set_error(DU_ERR_BAD_ARG, "du_guided_step: mask_period must divide the row length");
   if ((p->thr || p->guidance == DU_GUIDE_POSTERIOR) && !p->u) return set_error(DU_ERR_BAD_ARG, "du_guided_step: u required");
-  if ((p->guidance == DU_GUIDE_GRAD_BLEND || p->guidance == DU_GUIDE_GRAD_ADD) && !check_view(p->aux, p->aux_dtype))
+  if ((p->guidance == DU_GUIDE_GRAD_BLEND || p->guidance == DU_GUIDE_GRAD_ADD || p->guidance == DU_GUIDE_LINCOMB) && !check_view(p->aux, p->aux_dtype))
     return set_error(DU_ERR_BAD_ARG, "du_guided_step: gradient tensor required");
   if (p->aux && !dtype_ok(p->aux_dtype)) return set_error(DU_ERR_DTYPE, "du_guided_step: bad aux dtype");
   if (!p->prev_out && !p->x0_out && !p->eps_out && !p->mask_out) return set_error(DU_ERR_BAD_ARG, "du_guided_step: no output requested");
   if (p->skip_ddim && (p->prev_out || p->x0_out)) return set_error(DU_ERR_BAD_ARG, "du_guided_step: skip_ddim with prev/x0 outputs");
   GuidedF f{*p};
   int64_t n = p->n;
-  bool vec = (n % 4 == 0) && vec4_ok(p->eps, p->eps_stride, p->eps_dtype) &&
+  bool vec = (n % 4 == 0) && (p->mask_period % 4 == 0) && vec4_ok(p->eps, p->eps_stride, p->eps_dtype) &&
              (p->skip_ddim || vec4_ok(p->sample, p->sample_stride, p->sample_dtype)) && vec4_ok(p->u, p->u_stride, DU_F32) &&
              vec4_ok(p->mask, p->mask_stride, DU_F32) && vec4_ok(p->aux, p->aux_broadcast ? 0 : p->aux_stride, p->aux_dtype) &&
              vec4_ok(p->prev_out, p->prev_stride, p->prev_dtype) && vec4_ok(p->x0_out, p->x0_stride, p->x0_dtype) &&

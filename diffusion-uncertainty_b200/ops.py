@@ -17,7 +17,7 @@ _MODES = {"var": L.MOM_VAR_UNBIASED, "centered": L.MOM_CENTERED, "var_with_cente
           "raw": L.MOM_RAW, "std": L.MOM_STD_UNBIASED, "partial": L.MOM_PARTIAL_M2}
 _PRED = {"epsilon": L.PRED_EPSILON, "sample": L.PRED_SAMPLE, "v_prediction": L.PRED_V}
 _GUIDE = {"none": L.GUIDE_NONE, "posterior": L.GUIDE_POSTERIOR, "grad_blend": L.GUIDE_GRAD_BLEND,
-          "grad_add": L.GUIDE_GRAD_ADD, "weights": L.GUIDE_WEIGHTS}
+          "grad_add": L.GUIDE_GRAD_ADD, "weights": L.GUIDE_WEIGHTS, "lincomb": L.GUIDE_LINCOMB}
 _ZN = {"max": L.ZN_BELOW, "min": L.ZN_ABOVE, "below": L.ZN_BELOW, "above": L.ZN_ABOVE, "multiscale": L.ZN_MULTISCALE}
 
 # launches issued through this module since import (bench.py reports it as gpu_launches)
@@ -124,6 +124,161 @@ def moments(scores: Union[Sequence[torch.Tensor], torch.Tensor], center: Optiona
     L.check(rc)
     _count()
     return (out, mean) if return_mean else out
+
+
+def moments_backward(scores: Sequence[torch.Tensor], grad_u: torch.Tensor, mode: str = "var", center: Optional[torch.Tensor] = None,
+                     need: Optional[Sequence[bool]] = None, need_center: bool = False):
+    """Backward of `moments` (du_moments_backward): returns ([grad_scores[m] or None], grad_center or None), fp32.
+    `need[m]` = False skips the gradient of sample m."""
+    rows = [Rows(s_.detach(), f"scores[{k}]") for k, s_ in enumerate(scores)]
+    r0 = rows[0]
+    for r in rows[1:]:
+        _same_rows(r0, r, "moments_backward")
+    if len({(r.stride, r.dt) for r in rows}) != 1:
+        rows = [Rows(r.t.float().contiguous(), "scores") for r in rows]
+        r0 = rows[0]
+    g = Rows(grad_u.detach(), "grad_u"); _same_rows(r0, g, "moments_backward(grad_u)")
+    crow = None
+    if center is not None:
+        crow = Rows(center.detach(), "center"); _same_rows(r0, crow, "moments_backward(center)")
+    shape, dev = scores[0].shape, scores[0].device
+    need = [True] * len(rows) if need is None else list(need)
+    grads = [torch.empty(shape, device=dev, dtype=torch.float32) if nd else None for nd in need]
+    gc = torch.empty(shape, device=dev, dtype=torch.float32) if (need_center and crow is not None) else None
+    if r0.B * r0.n == 0:
+        return grads, gc
+    sp = (C.c_void_p * len(rows))(*[r.ptr for r in rows])
+    gp = (C.c_void_p * len(rows))(*[C.c_void_p(t.data_ptr()) if t is not None else NULL for t in grads])
+    L.check(L.load().du_moments_backward(sp, len(rows), r0.stride, r0.dt, crow.ptr if crow else NULL, crow.stride if crow else 0,
+                                         crow.dt if crow else 0, _MODES[mode], g.ptr, g.stride, g.dt, r0.B, r0.n, gp, r0.n,
+                                         L.F32, C.c_void_p(gc.data_ptr()) if gc is not None else NULL, r0.n, _stream(grad_u)))
+    _count()
+    return grads, gc
+
+
+class _MomentsFn(torch.autograd.Function):
+    """`moments` as a differentiable op: forward = du_moments, backward = du_moments_backward.  The schedulers that
+    differentiate the map through the score model (SU/scheduling_ddim_uncertainty_grad.py:536-538 and relatives) call it
+    through `moments_autograd`; the model's own backward stays torch autograd."""
+
+    @staticmethod
+    def forward(ctx, mode, center, *scores):
+        ctx.mode = mode
+        ctx.has_center = center is not None
+        ctx.save_for_backward(*([center] if center is not None else []), *scores)
+        return moments([s_.detach() for s_ in scores], center=center.detach() if center is not None else None, mode=mode,
+                       out_dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_u):
+        saved = ctx.saved_tensors
+        center = saved[0] if ctx.has_center else None
+        scores = saved[1:] if ctx.has_center else saved
+        need = list(ctx.needs_input_grad[2:])
+        need_c = ctx.has_center and ctx.needs_input_grad[1]
+        grads, gc = moments_backward(scores, grad_u.contiguous(), ctx.mode, center, need=need, need_center=need_c)
+        grads = [g_.to(s_.dtype) if g_ is not None else None for g_, s_ in zip(grads, scores)]
+        return (None, gc.to(center.dtype) if gc is not None else None, *grads)
+
+
+def moments_autograd(scores: Sequence[torch.Tensor], mode: str = "var", center: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable F1 reduction ('var' | 'centered' | 'var_with_center'), fp32 map."""
+    return _MomentsFn.apply(mode, center, *scores)
+
+
+# ------------------------------------------------------------------------------------------------ N4 flips
+def _chw(x: torch.Tensor):
+    if x.dim() != 4:
+        raise ValueError("flip ops expect [B, C, H, W] tensors")
+    return int(x.shape[1]), int(x.shape[2]), int(x.shape[3])
+
+
+def flip_h(x: torch.Tensor) -> torch.Tensor:
+    """torch.flip(x, dims=[2]) (du_flip_h) — the model input of the flipped forward, SU/scheduling_ddim_flip.py:487."""
+    r = Rows(x, "x")
+    Cc, H, W = _chw(x)
+    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    if out.numel() == 0:
+        return out
+    L.check(L.load().du_flip_h(r.ptr, r.stride, r.dt, r.B, Cc, H, W, C.c_void_p(out.data_ptr()), r.n, _DT[out.dtype], _stream(x)))
+    _count()
+    return out
+
+
+def flip_sqdiff(eps: torch.Tensor, flipped_output: torch.Tensor, channel_amax: bool = False,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(eps - flip_h(flipped_output))^2, optionally followed by amax over channels (keepdim) — du_flip_sqdiff,
+    SU/scheduling_ddim_flip.py:488-493, SU/scheduling_ddim_flip_threshold.py:504-506.  fp32 result."""
+    e, f = Rows(eps, "eps"), Rows(flipped_output, "flipped_output")
+    _same_rows(e, f, "flip_sqdiff")
+    Cc, H, W = _chw(eps)
+    shape = (eps.shape[0], 1, H, W) if channel_amax else tuple(eps.shape)
+    if out is None:
+        out = torch.empty(shape, device=eps.device, dtype=torch.float32)
+    orow = Rows(out, "out")
+    if orow.t is not out or out.dtype != torch.float32 or tuple(out.shape) != tuple(shape):
+        raise ValueError("flip_sqdiff: `out` must be a float32 tensor of the result shape with contiguous rows")
+    if out.numel() == 0:
+        return out
+    L.check(L.load().du_flip_sqdiff(e.ptr, e.stride, e.dt, f.ptr, f.stride, f.dt, e.B, Cc, H, W, int(channel_amax), orow.ptr, orow.stride,
+                                    _stream(eps)))
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ N2 / N3
+def column_kth(x: torch.Tensor, k: int) -> torch.Tensor:
+    """k-th smallest (0-based) over dim 0 of x [N, ...] per remaining position, NaN last (du_column_kth):
+    `x.gather(0, x.argsort(dim=0)[k].unsqueeze(0)).squeeze(0)` of scripts/compute_threshold_pixel_wise.py:90-100.
+    x may be a [:, i] slice of the [N, T_uc, C, H, W] accumulated maps (row stride = T_uc * C*H*W)."""
+    r = Rows(x, "x")
+    if r.B < 1 or not (0 <= int(k) < r.B):
+        raise IndexError(f"column_kth: k={k} out of range for {r.B} samples")
+    out = torch.empty(x.shape[1:], device=x.device, dtype=x.dtype)
+    L.check(L.load().du_column_kth(r.ptr, r.dt, r.B, r.n, r.stride, int(k), C.c_void_p(out.data_ptr()), _stream(x)))
+    _count()
+    return out
+
+
+def fit_pixel_thresholds(uncertainties: torch.Tensor, perc: float) -> torch.Tensor:
+    """The per-timestep / per-pixel thresholds of scripts/compute_threshold_pixel_wise.py:86-100: for uncertainties
+    [N, T_uc, C, H, W] returns [T_uc, C, H, W], the int(N * perc)-th smallest value over the samples at every timestep."""
+    N, T_ = int(uncertainties.shape[0]), int(uncertainties.shape[1])
+    k = int(N * perc)
+    return torch.stack([column_kth(uncertainties[:, i], k) for i in range(T_)], dim=0)
+
+
+def row_sum(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(dim=(1, 2, ...)) per sample as fp32 (du_row_sum) — scripts/uncertainty_benchmark_imagenet.py:314."""
+    _require_cuda(x, "x")
+    if x.shape[0] == 0 or x.numel() == 0:
+        return torch.zeros(x.shape[0], device=x.device, dtype=torch.float32)
+    flat = x.reshape(x.shape[0], -1) if x.is_contiguous() else x.contiguous().reshape(x.shape[0], -1)
+    r = Rows(flat, "x")
+    out = torch.zeros(r.B, device=x.device, dtype=torch.float32)
+    if r.B == 0 or r.n == 0:
+        return out
+    L.check(L.load().du_row_sum(r.ptr, r.stride, r.dt, r.B, r.n, C.c_void_p(out.data_ptr()), _stream(x)))
+    _count()
+    return out
+
+
+def slot_sum(x: torch.Tensor) -> torch.Tensor:
+    """x.sum(dim=1) of the accumulated maps [B, T_uc, ...] as fp32 (du_slot_sum) — scripts/compute_ause.py:128."""
+    _require_cuda(x, "x")
+    if x.dim() < 3:
+        raise ValueError("slot_sum expects [B, T, ...]")
+    x = x if x.is_contiguous() else x.contiguous()
+    B, T_ = int(x.shape[0]), int(x.shape[1])
+    n = 1
+    for d_ in x.shape[2:]:
+        n *= int(d_)
+    out = torch.zeros((B,) + tuple(x.shape[2:]), device=x.device, dtype=torch.float32)
+    if out.numel() == 0 or T_ == 0:
+        return out
+    L.check(L.load().du_slot_sum(C.c_void_p(x.data_ptr()), T_ * n, n, _DT[x.dtype], B, T_, n, C.c_void_p(out.data_ptr()), n, _stream(x)))
+    _count()
+    return out
 
 
 def moments_merge(means: Sequence[torch.Tensor], m2s: Sequence[torch.Tensor], counts: Sequence[int], mode: str = "var",
@@ -276,9 +431,10 @@ def guided_step(eps: torch.Tensor, sample: Optional[torch.Tensor], coeffs: Optio
                 u: Optional[torch.Tensor] = None, thr: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
                 aux: Optional[torch.Tensor] = None, aux_broadcast: bool = False, higher: bool = True, lam: float = 1.0,
                 post_M: float = 0.0, inv_alpha_hat: float = 0.0, want_prev: bool = True, want_x0: bool = False,
-                want_eps: bool = True, want_mask: bool = False):
+                want_eps: bool = True, want_mask: bool = False, x0_unguided: bool = False):
     """mask + guided score + DDIM update in one elementwise pass (du_guided_step).
-    Returns dict(prev, x0, eps, mask) with None for outputs not requested."""
+    Returns dict(prev, x0, eps, mask) with None for outputs not requested.  `mask` may be [B,1,H,W] against [B,C,H,W]
+    rows (broadcast over channels); x0_unguided: x0 from the unguided eps, direction from the guided one."""
     e = Rows(eps, "eps")
     P = L.GuidedParams()
     P.eps, P.eps_stride, P.eps_dtype, P.guidance = e.ptr, e.stride, e.dt, _GUIDE[guidance]
@@ -293,6 +449,7 @@ def guided_step(eps: torch.Tensor, sample: Optional[torch.Tensor], coeffs: Optio
         P.ddim = coeffs
     P.skip_ddim = int(skip)
     P.higher = int(higher)
+    P.x0_unguided = int(bool(x0_unguided))
     if u is not None:
         if u.dtype != torch.float32:
             u = u.float()
@@ -307,7 +464,13 @@ def guided_step(eps: torch.Tensor, sample: Optional[torch.Tensor], coeffs: Optio
     if mask is not None:
         if mask.dtype != torch.float32:
             mask = mask.float()
-        mr = Rows(mask, "mask"); _same_rows(e, mr, "guided_step(mask)"); keep.append(mr)
+        mr = Rows(mask, "mask"); keep.append(mr)
+        if mr.n != e.n:
+            if mr.B != e.B or mr.n == 0 or e.n % mr.n != 0:
+                raise ValueError("guided_step: a broadcast mask must hold a whole divisor of the elements of an image")
+            P.mask_period = mr.n
+        else:
+            _same_rows(e, mr, "guided_step(mask)")
         P.mask, P.mask_stride = mr.ptr, mr.stride
     if aux is not None:
         ar = Rows(aux, "aux", batch=not aux_broadcast); keep.append(ar)

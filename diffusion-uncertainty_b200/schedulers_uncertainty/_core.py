@@ -348,7 +348,8 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
         """sqrt(abar_t) x0 + sqrt(1-abar_t) n (…zigzag_centered.py:593-626).  A single timestep runs in du_perturb;
         per-sample timestep vectors (training-style use, off the hot path) broadcast in torch."""
         sa, sb = self._per_sample_scalars(timesteps, original_samples)
-        if sa.numel() == 1 and original_samples.is_cuda:
+        traced = torch.is_grad_enabled() and (original_samples.requires_grad or noise.requires_grad)   # gradient schedulers
+        if sa.numel() == 1 and original_samples.is_cuda and not traced:
             return ops.perturb(original_samples, noise, float(sa), float(sb))
         while sa.dim() < original_samples.dim():
             sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)

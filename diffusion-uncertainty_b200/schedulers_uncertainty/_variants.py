@@ -223,8 +223,12 @@ class ZNormThreshold(UncertaintyDDIMCore):
         """[mean, unbiased std, count, M2] over the WHOLE batch; hook for the multi-GPU merge (distributed.py)."""
         return ops.znorm_stats(u)
 
+    def _raw_map(self, st: StepState) -> torch.Tensor:
+        """the un-normalised map: torch.var over the M perturbed predictions (F1b)"""
+        return ops.moments(self._perturbed_scores(st), mode="var")
+
     def _uncertainty_block(self, st: StepState) -> torch.Tensor:
-        u = ops.moments(self._perturbed_scores(st), mode="var")
+        u = self._raw_map(st)
         stats = self._stats(u) if self.uncertainty_normalize else None
         mode = "multiscale" if self.multiscale else ("max" if self.uncertainty_threshold_mode == "max" else "min")
         z, w = ops.znorm_weights(u, stats, mode=mode, thr=float(self.uncertainty_threshold), normalize=self.uncertainty_normalize)
@@ -250,3 +254,115 @@ class MultiscaleThreshold(ZNormThreshold):
     @records_config
     def __init__(self, *args, uncertainty_normalize: bool = True, **kw):
         super().__init__(*args, uncertainty_normalize=uncertainty_normalize, **kw)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+class Flip(UncertaintyDDIMCore):
+    """`flip`.  scheduling_ddim_flip.py:486-493: ONE extra forward on the H-flipped x0 (`torch.flip(x0, dims=[2])`), the
+    prediction flipped back, u = (eps - flipped)^2 — no M axis.  Both flips and the squared difference run in
+    du_flip_h / du_flip_sqdiff (the flip back is folded into the difference kernel's addressing)."""
+
+    channel_amax = False
+
+    def _flip_map(self, st: StepState, out=None) -> torch.Tensor:
+        flipped_output = self.predict_model(ops.flip_h(st.x0), st.t)
+        eps = st.model_output if self.config.prediction_type == "epsilon" else st.eps
+        return ops.flip_sqdiff(eps, flipped_output, channel_amax=self.channel_amax, out=out)
+
+    def _uncertainty_block(self, st: StepState) -> torch.Tensor:
+        return self._flip_map(st, out=self._map_out(st.x0, torch.float32))
+
+
+class FlipThreshold(ZNormThreshold):
+    """fid:`flip_threshold`.  scheduling_ddim_flip_threshold.py:497-561: flip map -> amax over channels ([B,1,H,W]) ->
+    whole-batch z-norm -> scalar threshold mask -> eps * mask (broadcast over channels) -> x0 from the UNMASKED
+    prediction -> x_{t-1} again (F4)."""
+
+    @records_config
+    def __init__(self, *args, uncertainty_scale: float = 0.9, **kw):
+        super().__init__(*args, **kw)
+        self.uncertainty_scale = uncertainty_scale
+
+    def _raw_map(self, st: StepState) -> torch.Tensor:
+        flipped_output = self.predict_model(ops.flip_h(st.x0), st.t)
+        return ops.flip_sqdiff(st.model_output, flipped_output, channel_amax=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+class UncertaintyGrad(UncertaintyDDIMCore):
+    """fid:`uncertainty_grad`.  scheduling_ddim_uncertainty_grad.py:518-570: the map (torch.var over M re-noised forwards) is
+    differentiated through the score model with respect to eps; eps' = eps + grad * abar_t; x0 from the UNGUIDED
+    prediction; x_{t-1} recomputed (eta noise not re-added).  The reduction and its backward are du_moments /
+    du_moments_backward (ops.moments_autograd), the blend + DDIM update one du_guided_step launch; the model's own
+    backward is torch autograd.  Only predict_next=False is live in the reference (with predict_next the gradient is None
+    and the reference's assert fires): the same AssertionError is raised here."""
+
+    def _uncertainty_block(self, st: StepState) -> torch.Tensor:
+        assert not self.predict_next, "grad_pred_epsilon is None: the reference asserts when predict_next=True"
+        h = st.host
+        sb, sa = h["sqrt_beta_t"], h["sqrt_alpha_t"]
+        with torch.enable_grad():
+            e = st.eps.detach().clone().requires_grad_(True)
+            x0 = (st.sample - sb * e) / sa                      # :522, traced for autograd (model-input side)
+            scores = []
+            for _ in range(self.M):
+                noise = torch.randn_like(x0)
+                x_hat = self.scale_model_input(self.add_noise(x0, noise, st.t), st.t)
+                scores.append(self.predict_model(x_hat, st.t))
+            u = ops.moments_autograd(scores, "var")
+            u.mean(dim=0).sum().backward()
+        g = e.grad
+        assert g is not None
+        c = ops.make_coeffs(h["sqrt_alpha_t"], h["sqrt_beta_t"], h["sqrt_alpha_prev"], h["dir_coef"],
+                            clip_sample=bool(self.config.clip_sample), clip_range=float(self.config.clip_sample_range),
+                            use_clipped_model_output=st.use_clipped)
+        r = ops.guided_step(st.eps, st.sample, c, guidance="grad_add", aux=g, lam=float(h["alpha_prod_t"]), x0_unguided=True,
+                            want_prev=True, want_x0=True, want_eps=True)
+        if self.config.prediction_type == "epsilon":
+            # x0 comes from model_output (:552); for epsilon prediction st.eps IS model_output
+            pass
+        st.prev, st.x0, st.eps = r["prev"], r["x0"], r["eps"]
+        u = u.detach()
+        sink = self._map_out(u)
+        if sink is not None:
+            ops.accumulate_slot(u, sink)
+            u = sink
+        return u
+
+
+class MCDropoutGradient(MCDropout):
+    """fid:`mc_dropout_gradient`.  scheduling_ddim_mc_dropout_gradient.py:490-549: M dropout forwards of the SAME sample under
+    autograd, gradient of the map with respect to the sample, eps' = 0.9 eps + 0.1 grad, x0 recomputed from the model
+    output WITHOUT clipping, then the ordinary x_{t-1} (eta noise from `variance_noise`)."""
+
+    def _before_update(self, st: StepState) -> torch.Tensor:
+        self.unet.train()
+        try:
+            with torch.enable_grad():
+                sg = st.sample.detach().clone().requires_grad_(True)
+                scores = [self.predict_model(sg, st.t) for _ in range(self.M)]
+                u = ops.moments_autograd(scores, "var")
+                u.mean(dim=0).sum().backward()
+            self._grad_sample = sg.grad
+            assert self._grad_sample is not None
+        finally:
+            self.unet.eval()
+        u = u.detach()
+        sink = self._map_out(u)
+        if sink is not None:
+            ops.accumulate_slot(u, sink)
+            u = sink
+        return u
+
+    def _ddim_update(self, st: StepState, noise):
+        if not self.in_window(st.t):
+            return super()._ddim_update(st, noise)
+        h = st.host
+        c = ops.make_coeffs(h["sqrt_alpha_t"], h["sqrt_beta_t"], h["sqrt_alpha_prev"], h["dir_coef"], clip_sample=False,
+                            use_clipped_model_output=st.use_clipped)
+        r = ops.guided_step(st.model_output, st.sample, c, guidance="lincomb", aux=self._grad_sample, post_M=0.9, lam=0.1,
+                            x0_unguided=True, want_prev=True, want_x0=True, want_eps=True)
+        prev = r["prev"]
+        if noise is not None:
+            prev = ops.perturb(prev, noise, 1.0, h["sigma"])
+        st.prev, st.x0, st.eps = prev, r["x0"], r["eps"]

@@ -1,7 +1,8 @@
 """String -> scheduler factory.  Mirrors diffusion_uncertainty/schedulers_uncertainty/get_uncertainty_scheduler.py:13-40
 (same `--scheduler-type` keys, same argparse attribute names, unknown keys fall through to MC-dropout).  Keys whose
-scheduler is outside the hot-path scope (`flip`, `flip_grad`: one extra forward / autograd, SURVEY.md §8f N4;
+scheduler is outside the hot-path scope (`flip_grad`: per-parameter gradients upsampled to a map, autograd only;
 `dpm_2_uncertainty_centered`) raise NotImplementedError naming the row instead of silently picking another scheduler."""
+from .scheduling_ddim_flip import DDIMSchedulerUncertaintyImagenetClassConditioned as _Flip
 from .scheduling_ddim_mc_dropout import DDIMSchedulerUncertaintyImagenetClassConditioned as _MCDropout
 from .scheduling_ddim_uncertainty import DDIMSchedulerUncertaintyImagenetClassConditioned as _Uncertainty
 from .scheduling_ddim_uncertainty_centered import DDIMSchedulerUncertaintyImagenetClassConditioned as _Centered
@@ -9,7 +10,7 @@ from .scheduling_ddim_uncertainty_centered_d import DDIMSchedulerUncertaintyImag
 from .scheduling_ddim_uncertainty_image import DDIMSchedulerUncertaintyImagenetClassConditioned as _Image
 from .scheduling_ddim_uncertainty_zigzag_centered import DDIMSchedulerUncertaintyImagenetClassConditioned as _ZigZagCentered
 
-_NOT_ON_PATH = {"flip", "flip_grad", "dpm_2_uncertainty_centered"}
+_NOT_ON_PATH = {"flip_grad", "dpm_2_uncertainty_centered"}
 
 
 def get_uncertainty_scheduler(args, y, unet, scheduler):
@@ -18,6 +19,9 @@ def get_uncertainty_scheduler(args, y, unet, scheduler):
     common = dict(after_step=args.start_step_uc, num_steps_uc=args.num_steps_uc, unet=unet, y=y, eta=getattr(args, "eta", 0.0))
     if kind in _NOT_ON_PATH:
         raise NotImplementedError(f"scheduler type {kind!r} is outside the accelerated uncertainty path (SURVEY.md §8f)")
+    if kind == "flip":
+        return _Flip.from_config(cfg, after_step=args.start_step_uc, num_steps_uc=args.num_steps_uc, unet=unet,
+                                 eta=getattr(args, "eta", 0.0), prompt_embeds=y)
     if kind == "uncertainty":
         return _Uncertainty.from_config(cfg, M=args.M, predict_next=args.predict_next, **common)
     if kind == "uncertainty_image":

@@ -173,11 +173,16 @@ int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_dtype,
  *   GRAD_BLEND PU/...guided_gradient.py:117-118        eps(1-m) + (eps + lam*g) m
  *   GRAD_ADD   uncertainty_guidance.py:129             eps + lam*g*m
  *   WEIGHTS    SU/scheduling_ddim_uncertainty_threshold.py:554-574   eps*w; x0 from the UNMASKED eps
+ *   LINCOMB    SU/scheduling_ddim_mc_dropout_gradient.py:514         post_M*eps + lam*g   (post_M carries the eps weight)
  *   NONE       plain F3
+ * x0_unguided != 0: x0 is computed from the UNGUIDED eps and only the direction term uses eps' — what every in-scheduler
+ * guidance of the reference does (SU/scheduling_ddim_uncertainty_grad.py:551-570, ..._mc_dropout_gradient.py:514-515,
+ * ..._model_gradient_guided.py:554-562); WEIGHTS always behaves that way.  GRAD_ADD / LINCOMB need no mask (m = 1).
  * mask source: per-row threshold thr[B] compared with u (strict; `higher`), or an explicit fp32
  * mask/weight tensor.
  * ---------------------------------------------------------------------------------------------- */
-enum du_guidance { DU_GUIDE_NONE = 0, DU_GUIDE_POSTERIOR = 1, DU_GUIDE_GRAD_BLEND = 2, DU_GUIDE_GRAD_ADD = 3, DU_GUIDE_WEIGHTS = 4 };
+enum du_guidance { DU_GUIDE_NONE = 0, DU_GUIDE_POSTERIOR = 1, DU_GUIDE_GRAD_BLEND = 2, DU_GUIDE_GRAD_ADD = 3, DU_GUIDE_WEIGHTS = 4,
+                   DU_GUIDE_LINCOMB = 5 };
 
 typedef struct du_guided_params {
   /* inputs */
@@ -197,9 +202,11 @@ typedef struct du_guided_params {
   int64_t B, n;
   /* outputs, all nullable */
   void* prev_out;       int64_t prev_stride;   int32_t prev_dtype;   int32_t _pad0;
-  void* x0_out;         int64_t x0_stride;     int32_t x0_dtype;     int32_t _pad1;
+  void* x0_out;         int64_t x0_stride;     int32_t x0_dtype;     int32_t x0_unguided;
   void* eps_out;        int64_t eps_out_stride; int32_t eps_out_dtype; int32_t _pad2;
   float* mask_out;      int64_t mask_out_stride;
+  int64_t mask_period;                         /* > 0: mask rows hold mask_period elements, element i uses mask[i % mask_period]
+                                                  (a [B,1,H,W] mask over [B,C,H,W] rows); 0: same length as the rows */
 } du_guided_params;
 
 int du_guided_step(const du_guided_params* p, du_stream_t stream);
@@ -261,6 +268,49 @@ int du_fused_supported(int64_t n, int score_dtype);
  * kernel (fused_step_kernel), 2 = the predictive single-pass kernel (fused_pred_kernel; slices of >= 4 trips with the
  * epsilon-prediction fp32 update).  Both give bit-identical results; benchmarks use this to name what they timed. */
 int du_fused_last_kernel(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * N4 — flip-based uncertainty.  Tensors are [B, C, H, W] rows views (row = C*H*W elements).
+ * du_flip_h: out[b,c,h,w] = x[b,c,H-1-h,w]  — torch.flip(x0, dims=[2]), the model input of the flipped forward
+ *   (SU/scheduling_ddim_flip.py:487).
+ * du_flip_sqdiff: u = (eps - flip_h(flipped_output))^2 (SU/scheduling_ddim_flip.py:488-493); channel_amax != 0 also reduces
+ *   with amax over C (NaN-propagating) into rows of H*W elements (SU/scheduling_ddim_flip_threshold.py:504-506).
+ * ---------------------------------------------------------------------------------------------- */
+int du_flip_h(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t C, int64_t H, int64_t W,
+              void* out, int64_t out_stride, int out_dtype, du_stream_t stream);
+int du_flip_sqdiff(const void* eps, int64_t eps_stride, int eps_dtype, const void* flipped, int64_t f_stride, int f_dtype,
+                   int64_t B, int64_t C, int64_t H, int64_t W, int channel_amax, float* out, int64_t out_stride,
+                   du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * F6 — backward of du_moments for the schedulers / pipelines that differentiate the map through the score model
+ * (`uncertainty.mean(dim=0).sum().backward()`: SU/scheduling_ddim_uncertainty_grad.py:536-538,
+ * SU/scheduling_ddim_mc_dropout_gradient.py:499-503, SU/scheduling_ddim_model_gradient_guided.py:546-548,
+ * PU/pipeline_sampler_class_conditional_uncertainty_guided_gradient.py:190-194).  grad_scores[m] = grad_u * d u / d s_m for
+ * modes VAR_UNBIASED, CENTERED, VAR_WITH_CENTER; grad_center (nullable) = grad_u * d u / d center.  grad_scores[m] may be
+ * NULL for samples that need no gradient.  The score model's own backward stays torch autograd.
+ * ---------------------------------------------------------------------------------------------- */
+int du_moments_backward(const void* const* scores, int M, int64_t score_stride, int score_dtype, const void* center,
+                        int64_t center_stride, int center_dtype, int mode, const void* grad_u, int64_t gu_stride,
+                        int gu_dtype, int64_t B, int64_t n, void* const* grad_scores, int64_t grad_stride,
+                        int grad_dtype, void* grad_center, int64_t gc_stride, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N2 — per-pixel threshold fitting: out[j] = the k-th smallest (0-based) of x[0..N-1][j] over the sample axis, NaN last,
+ * i.e. uncertainties_timestep.gather(0, uncertainties_timestep.argsort(dim=0)[k]) with k = int(num_samples * perc)
+ * (scripts/compute_threshold_pixel_wise.py:90-100, 143-152).  x: [N, n] with row stride `row_stride` elements (a [:, i]
+ * slice of the [N, T_uc, C, H, W] accumulated maps); out: [n], same dtype.
+ * ---------------------------------------------------------------------------------------------- */
+int du_column_kth(const void* x, int dtype, int64_t N, int64_t n, int64_t row_stride, int64_t k, void* out, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * N3 — per-image reductions of the accumulated map: du_row_sum: out[b] = sum of row b (uncertainty.sum(dim=(1,2,3,4)),
+ * scripts/uncertainty_benchmark_imagenet.py:314); du_slot_sum: out[b, :] = sum over the T slots of [B, T, n]
+ * (uncertainty.sum(dim=1), scripts/compute_ause.py:128).  fp32 accumulation in a fixed order.
+ * ---------------------------------------------------------------------------------------------- */
+int du_row_sum(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, float* out, du_stream_t stream);
+int du_slot_sum(const void* x, int64_t x_stride, int64_t slot_stride, int x_dtype, int64_t B, int T, int64_t n,
+                float* out, int64_t out_stride, du_stream_t stream);
 
 #ifdef __cplusplus
 }

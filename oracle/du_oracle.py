@@ -318,6 +318,25 @@ def uncertainty_step_znorm(scores: Sequence[Tensor], eps: Tensor, sample: Tensor
 # --------------------------------------------------------------------------------------------
 # Whole scheduler step (L3), restated per variant from the F-rows above
 # --------------------------------------------------------------------------------------------
+def flip_uncertainty(eps: Tensor, flipped_back_output: Tensor, channel_amax: bool = False) -> Tensor:
+    """SU/scheduling_ddim_flip.py:493 `(pred_epsilon - flipped_output).pow(2)`; flip_threshold.py:506 adds
+    `.amax(dim=1, keepdim=True)`.  `flipped_back_output` is already flipped back (dims=[2])."""
+    u = (eps - flipped_back_output).pow(2)
+    return u.amax(dim=1, keepdim=True) if channel_amax else u
+
+
+def column_kth(x: Tensor, k: int) -> Tensor:
+    """scripts/compute_threshold_pixel_wise.py:90-100: value at argsort(dim=0)[k] per position."""
+    idx = x.argsort(dim=0)[k].unsqueeze(0)
+    return x.gather(dim=0, index=idx).squeeze(0)
+
+
+def fit_pixel_thresholds(uncertainties: Tensor, perc: float) -> Tensor:
+    """scripts/compute_threshold_pixel_wise.py:86-100 for uncertainties [N, T_uc, C, H, W]."""
+    n = uncertainties.shape[0]
+    return torch.stack([column_kth(uncertainties[:, i], int(n * perc)) for i in range(uncertainties.shape[1])], dim=0)
+
+
 class OracleOutput:
     def __init__(self, prev_sample, pred_original_sample, uncertainty=None, pred_epsilon=None):
         self.prev_sample = prev_sample
@@ -337,6 +356,10 @@ class OracleScheduler:
     'mc_dropout'           scheduling_ddim_mc_dropout.py                             :455-556
     'threshold'            scheduling_ddim_uncertainty_threshold.py                  :455-583
     'multiscale'           scheduling_ddim_infer_noise_multiscale_threshold.py       :455-578
+    'flip'                 scheduling_ddim_flip.py                                   :440-530
+    'flip_threshold'       scheduling_ddim_flip_threshold.py                         :441-583
+    'uncertainty_grad'     scheduling_ddim_uncertainty_grad.py                       :455-585 (predict_next=False: the only live mode)
+    'mc_dropout_gradient'  scheduling_ddim_mc_dropout_gradient.py                    :440-549
     `predict(x, t)` is the model call (`predict_model`, SU/traits.py:8-18)."""
 
     def __init__(self, variant: str, predict, M: int, after_step: int, num_steps_uc: int, num_zigzag: int = 4,
@@ -379,6 +402,33 @@ class OracleScheduler:
         c = DDIMCoeffs(self.alphas_cumprod, self.final_alpha_cumprod, t, prev_t, eta)
         in_window = self.timestep_end_step <= t <= self.timestep_after_step
         v = self.variant
+        if v == "mc_dropout_gradient":
+            # M dropout forwards of the SAME sample under autograd, gradient of the map w.r.t. the sample (:490-515);
+            # inside the window x0 is recomputed from the model output WITHOUT clipping (:515)
+            u = g = None
+            if in_window:
+                self.unet.train()
+                with torch.enable_grad():
+                    sg = sample.detach().clone().requires_grad_(True)
+                    u = torch.var(torch.stack([self.predict(sg, t) for _ in range(self.M)], dim=0), dim=0)
+                    u.mean(dim=0).sum().backward()
+                g = sg.grad
+                self.unet.eval()
+            noise = None
+            if eta > 0:
+                noise = variance_noise if variance_noise is not None else torch.randn(model_output.shape)
+            prev, x0, eps = ddim_step(model_output, sample, c, self.prediction_type, self.clip_sample, self.clip_range,
+                                      eta, noise, use_clipped_model_output)
+            if in_window:
+                eps = 0.9 * model_output + 0.1 * g
+                x0 = (sample - c.sqrt_beta_t * model_output) / c.sqrt_alpha_t
+                if use_clipped_model_output:
+                    eps = (sample - c.sqrt_alpha_t * x0) / c.sqrt_beta_t
+                prev = c.sqrt_alpha_prev * x0 + c.dir_coef * eps
+                if eta > 0:
+                    prev = prev + c.sigma * noise
+            return OracleOutput(prev, x0, u.detach() if u is not None else None, eps if in_window else None)
+
         if v == "mc_dropout":
             # no best_noise draw; M dropout forwards on the SAME sample happen before the update
             u = None
@@ -398,6 +448,39 @@ class OracleScheduler:
                                   eta, best_noise, use_clipped_model_output)
         if not in_window:
             return OracleOutput(prev, x0)
+
+        if v in ("flip", "flip_threshold"):
+            # one forward on the H-flipped x0, flipped back (flip.py:486-493)
+            f = torch.flip(self.predict(torch.flip(x0, dims=[2]), t), dims=[2])
+            u = flip_uncertainty(eps, f, channel_amax=(v == "flip_threshold"))
+            if v == "flip":
+                return OracleOutput(prev, x0, u, eps)
+            z = znorm(u) if self.normalize else u                                   # flip_threshold.py:521-522
+            w = znorm_threshold_mask(z, self.thr, self.thr_mode)                    # :536-541 ([B,1,H,W], broadcast over C)
+            prev2, x02, eps2 = masked_restep(model_output, sample, w, c, self.clip_sample, self.clip_range,
+                                             use_clipped_model_output)              # :541-561
+            return OracleOutput(prev2, x02, z, eps2)
+
+        if v == "uncertainty_grad":
+            # scheduling_ddim_uncertainty_grad.py:518-570: the map is differentiated through the score model w.r.t. eps
+            with torch.enable_grad():
+                e = eps.detach().clone().requires_grad_(True)
+                x0g = (sample - c.sqrt_beta_t * e) / c.sqrt_alpha_t
+                sc = []
+                for _ in range(self.M):
+                    noise = torch.randn_like(x0g)
+                    sc.append(self.predict(perturb_add_noise(x0g, noise, self.alphas_cumprod[t]), t))
+                u = torch.var(torch.stack(sc, dim=0), dim=0)
+                u.mean(dim=0).sum().backward()
+            g = e.grad
+            eps2 = eps + g * c.alpha_prod_t
+            x02 = (sample - c.sqrt_beta_t * model_output) / c.sqrt_alpha_t
+            if self.clip_sample:
+                x02 = x02.clamp(-self.clip_range, self.clip_range)
+            if use_clipped_model_output:
+                eps2 = (sample - c.sqrt_alpha_t * x02) / c.sqrt_beta_t
+            prev2 = c.sqrt_alpha_prev * x02 + c.dir_coef * eps2
+            return OracleOutput(prev2, x02, u.detach(), eps2)
 
         scores = []
         if v in ("zigzag_centered", "zigzag"):

@@ -71,6 +71,39 @@ def run_scheduler_case(name, module, cls_name, ctor_kw, n_steps, B=4, C=3, H=16,
          timesteps=sched.timesteps, after=sched.timestep_after_step, end=sched.timestep_end_step)
 
 
+def main_widen():
+    """Fixtures of the rows added after the core path: flip / flip_threshold, the gradient schedulers and the
+    per-pixel threshold fitting.  `python tests/golden/make_golden.py widen` writes only these."""
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    run_scheduler_case("sched_flip", "scheduling_ddim_flip", "DDIMSchedulerUncertaintyImagenet",
+                       dict(after_step=10, num_steps_uc=5), n_steps=20, seed=10)
+    run_scheduler_case("sched_flip_threshold", "scheduling_ddim_flip_threshold",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(after_step=10, num_steps_uc=5, uncertainty_threshold=0.5, uncertainty_threshold_mode="max"),
+                       n_steps=20, seed=11)
+    run_scheduler_case("sched_uncertainty_grad", "scheduling_ddim_uncertainty_grad",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=4, after_step=10, num_steps_uc=5, predict_next=False), n_steps=20, seed=12)
+    run_scheduler_case("sched_mc_dropout_gradient", "scheduling_ddim_mc_dropout_gradient",
+                       "DDIMSchedulerUncertaintyImagenetClassConditioned",
+                       dict(M=4, after_step=10, num_steps_uc=5), n_steps=20, seed=13, dropout=True)
+    # N2: the expressions of scripts/compute_threshold_pixel_wise.py:89-100 (the script has no importable function for them)
+    g = torch.Generator().manual_seed(21)
+    unc = torch.rand(37, 3, 3, 8, 8, generator=g) ** 3
+    unc[5, 1, 0, 0, 0] = float("nan")
+    out = {}
+    for perc in (0.15, 0.9):
+        thr = []
+        for i in range(unc.shape[1]):
+            uncertainties_timestep = unc[:, i]
+            i_uncertaintities = uncertainties_timestep.argsort(dim=0)
+            i_perc_th = i_uncertaintities[int(unc.shape[0] * perc)].unsqueeze(0)
+            thr.append(uncertainties_timestep.gather(dim=0, index=i_perc_th).squeeze(0))
+        out[f"thr_{perc}"] = torch.stack(thr, dim=0)
+    save("pixel_thresholds", unc=unc, **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
@@ -194,4 +227,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "widen":
+        main_widen()
+    else:
+        main()

@@ -231,8 +231,12 @@ def test_factory_keys():
     args.scheduler_type = "uncertainty_centered_d"
     assert get_uncertainty_scheduler(args, "y", "unet", base).uncertainty_distance == 7
     args.scheduler_type = "flip"
-    with pytest.raises(NotImplementedError):
-        get_uncertainty_scheduler(args, "y", "unet", base)
+    fl = get_uncertainty_scheduler(args, "y", "unet", base)
+    assert "Flip" in [c.__name__ for c in type(fl).__mro__] and fl.config.after_step == 3 and fl.prompt_embeds == "y"
+    for key in ("flip_grad", "dpm_2_uncertainty_centered"):
+        args.scheduler_type = key
+        with pytest.raises(NotImplementedError):
+            get_uncertainty_scheduler(args, "y", "unet", base)
     assert instatiate_uc_scheduler is get_uncertainty_scheduler and instatiate_uncertainty_scheduler is get_uncertainty_scheduler
 
 

@@ -41,7 +41,15 @@ SCHED_CASES = [
     ("sched_threshold_min", "threshold", dict(M=5, after_step=10, num_steps_uc=5, uncertainty_threshold=0.5,
                                               uncertainty_threshold_mode="min", predict_next=True), 20, 8, 0.0, False, {}),
     ("sched_multiscale", "multiscale", dict(M=5, after_step=10, num_steps_uc=5), 20, 9, 0.0, False, {}),
+    # rows added after the core path (tests/golden/make_golden.py widen)
+    ("sched_flip", "flip", dict(M=1, after_step=10, num_steps_uc=5), 20, 10, 0.0, False, {}),
+    ("sched_flip_threshold", "flip_threshold", dict(M=1, after_step=10, num_steps_uc=5, uncertainty_threshold=0.5,
+                                                    uncertainty_threshold_mode="max"), 20, 11, 0.0, False, {}),
+    ("sched_uncertainty_grad", "uncertainty_grad", dict(M=4, after_step=10, num_steps_uc=5, predict_next=False), 20, 12, 0.0, False, {}),
+    ("sched_mc_dropout_gradient", "mc_dropout_gradient", dict(M=4, after_step=10, num_steps_uc=5), 20, 13, 0.0, True, {}),
 ]
+# the reference's `flip` fixture was recorded with DDIMSchedulerUncertaintyImagenet, whose predict_model passes no class label
+NO_LABEL_VARIANTS = ("flip",)
 
 
 @pytest.mark.parametrize("case", SCHED_CASES, ids=[c[0] for c in SCHED_CASES])
@@ -51,7 +59,8 @@ def test_oracle_scheduler_matches_reference(golden_dir, case):
     model = ToyADM(3, seed=seed, dropout=dropout).eval()
     x_T, y = T(g["x_T"]), T(g["y"])
     sched = O.OracleScheduler(variant, None, unet=model, **kw, **cfg)
-    sched.predict = lambda x, t: model(x, t, y=sched.prompt_embeds)[:, :3]
+    sched.predict = (lambda x, t: model(x, t)[:, :3]) if variant in NO_LABEL_VARIANTS else \
+        (lambda x, t: model(x, t, y=sched.prompt_embeds)[:, :3])
     sched.set_timesteps(n_steps)
     assert sched.timestep_after_step == int(g["after"]) and sched.timestep_end_step == int(g["end"])
     assert same(sched.timesteps.numpy(), g["timesteps"])

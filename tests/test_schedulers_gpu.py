@@ -25,7 +25,10 @@ SU = "diffusion_uncertainty_b200.schedulers_uncertainty."
 MODULE_OF = {"zigzag_centered": "scheduling_ddim_uncertainty_zigzag_centered", "zigzag": "scheduling_ddim_uncertainty_zigzag",
              "centered": "scheduling_ddim_uncertainty_centered", "infer_noise": "scheduling_ddim_infer_noise",
              "mc_dropout": "scheduling_ddim_mc_dropout", "threshold": "scheduling_ddim_uncertainty_threshold",
-             "multiscale": "scheduling_ddim_infer_noise_multiscale_threshold"}
+             "multiscale": "scheduling_ddim_infer_noise_multiscale_threshold", "flip": "scheduling_ddim_flip",
+             "flip_threshold": "scheduling_ddim_flip_threshold", "uncertainty_grad": "scheduling_ddim_uncertainty_grad",
+             "mc_dropout_gradient": "scheduling_ddim_mc_dropout_gradient"}
+CLASS_OF = {"flip": "DDIMSchedulerUncertaintyImagenet"}   # recorded without class labels (tests/test_oracle_golden.NO_LABEL_VARIANTS)
 
 
 def dev():
@@ -49,7 +52,8 @@ def build(case):
     name, variant, kw, n_steps, seed, eta, dropout, cfg = case
     mod = importlib.import_module(SU + MODULE_OF[variant])
     model = ToyADM(3, seed=seed, dropout=dropout).eval().to(dev())
-    sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
+    kw = {k: v for k, v in kw.items() if not (variant in ("flip", "flip_threshold") and k == "M")}
+    sched = getattr(mod, CLASS_OF.get(variant, "DDIMSchedulerUncertaintyImagenetClassConditioned")).from_config(
         {**dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True,
                 set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", timestep_spacing="leading"), **cfg},
         unet=model, **kw)
@@ -67,12 +71,21 @@ def test_scheduler_replays_the_reference_trajectory(golden_dir, case):
     with seeded_noise(1000 + seed):
         res = l4_sampling_loop(sched, model, x_T, y, eta=eta)
     assert res["uncertainty"].shape == g["uncertainty"].shape
-    feeds_back = variant in ("threshold", "multiscale")
-    if not feeds_back:
+    feeds_back = variant in ("threshold", "multiscale", "flip_threshold")
+    if variant in ("uncertainty_grad", "mc_dropout_gradient"):
+        # the map's gradient goes through du_moments_backward and torch autograd of the toy model: same formula as
+        # torch.var's backward, different rounding order -> fp32 tolerance on everything downstream of the gradient
+        assert rel_close(res["uncertainty"], g["uncertainty"], 1e-5, atol=1e-12)
+        assert rel_close(res["score"], g["score"], 1e-4, atol=1e-6)
+        assert rel_close(res["final"], g["final"], 1e-4, atol=1e-5)
+        assert same(res["prevs"][0].numpy(), g["prev_first"])      # before the window: plain DDIM, bit-exact
+    elif not feeds_back:
         assert same(res["final"].numpy(), g["final"]), "x_{t-1} trajectory must be bit-exact"
         assert same(res["score"].numpy(), g["score"])
         keep = [0, len(res["prevs"]) // 2]
         assert same(res["prevs"][keep[0]].numpy(), g["prev_first"]) and same(res["prevs"][keep[1]].numpy(), g["prev_mid"])
+        if variant == "flip":
+            assert same(res["uncertainty"].numpy(), g["uncertainty"]), "(eps - flip(eps_hat))^2 is one sub and one mul: bit-exact"
         assert rel_close(res["uncertainty"], g["uncertainty"], 1e-5, atol=1e-12)
     else:
         # z-normalised map: mean / std are whole-batch reductions -> absolute tolerance on the z scale
