@@ -22,7 +22,14 @@ from .schedulers_uncertainty.mixin import SchedulerUncertaintyMixin
 
 
 def predict_model(model, x, t_tensor, y):
-    """ADM call convention of the reference loops (generate_samples.py:186): learned-sigma head dropped."""
+    """Model dispatch of the reference loops (generate_samples.py:670-676): diffusers UNet2DModel -> `.sample`, UViTAE ->
+    positional class label, anything else the ADM convention with the learned-sigma head dropped.  Matched by class name so
+    that neither diffusers nor the U-ViT package has to be importable."""
+    names = {c.__name__ for c in type(model).__mro__}
+    if "UNet2DModel" in names:
+        return model(x, t_tensor).sample
+    if "UViTAE" in names:
+        return model(x, t_tensor, y)
     return model(x, t_tensor, y=y)[:, :3]
 
 

@@ -325,6 +325,26 @@ def flip_uncertainty(eps: Tensor, flipped_back_output: Tensor, channel_amax: boo
     return u.amax(dim=1, keepdim=True) if channel_amax else u
 
 
+def gradient_score_update(predict, input: Tensor, noisy_residual: Tensor, noise_like: Tensor, M: int, alpha_hat_t,
+                          gradient_wrt: str = "input"):
+    """PU/pipeline_sampler_class_conditional_uncertainty_guided_gradient.py:159-210 `estimate_score_update`:
+    returns (pixel_wise_uncertainty, update_scores).  `predict(x)` is predict_model(model, x, t_tensor, y_slice)."""
+    from math import sqrt
+    noisy_residual = noisy_residual.detach().clone().requires_grad_(gradient_wrt == "score")
+    input = input.detach().clone().requires_grad_(gradient_wrt == "input")
+    with torch.enable_grad():
+        pred_epsilon = predict(input)
+        pred_epsilon.mean(dim=0).sum().backward()                                                   # :182-183
+        pred_x_0 = (input - sqrt(1 - alpha_hat_t) * noisy_residual) / sqrt(alpha_hat_t)             # :184
+        preds = []
+        for _ in range(M):
+            x_hat_t = sqrt(alpha_hat_t) * pred_x_0 + sqrt(1 - alpha_hat_t) * torch.randn_like(noise_like)   # :187
+            preds.append(predict(x_hat_t))
+        u = (torch.stack(preds, dim=0) - noisy_residual.unsqueeze(0)).pow(2).mean(dim=0)            # :192
+        u.mean(dim=0).sum().backward()                                                              # :193-194
+    return u.detach(), (input.grad if gradient_wrt == "input" else noisy_residual.grad)
+
+
 def column_kth(x: Tensor, k: int) -> Tensor:
     """scripts/compute_threshold_pixel_wise.py:90-100: value at argsort(dim=0)[k] per position."""
     idx = x.argsort(dim=0)[k].unsqueeze(0)

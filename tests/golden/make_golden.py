@@ -23,7 +23,7 @@ sys.path.insert(0, "/root/reference")
 sys.path.insert(0, ROOT)
 
 from tests.helpers import l4_sampling_loop  # noqa: E402
-from tests.toy_models import ToyADM, ToySDUNet, seeded_noise  # noqa: E402
+from tests.toy_models import ToyADM, ToyADMWithParameter, ToySDUNet, seeded_noise  # noqa: E402
 
 SU = "diffusion_uncertainty.schedulers_uncertainty."
 
@@ -102,6 +102,32 @@ def main_widen():
             thr.append(uncertainties_timestep.gather(dim=0, index=i_perc_th).squeeze(0))
         out[f"thr_{perc}"] = torch.stack(thr, dim=0)
     save("pixel_thresholds", unc=unc, **out)
+
+    # F6: DiffusionClassConditionalGuidedGradient.estimate_score_update (both gradient targets) + the blend lines :114-118
+    from diffusion_uncertainty.pipeline_uncertainty import pipeline_sampler_class_conditional_uncertainty_guided_gradient as gg
+    from diffusion_uncertainty.pipeline_uncertainty import \
+        pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution as pd
+    model = ToyADMWithParameter(3, seed=14).eval()
+    g = torch.Generator().manual_seed(14)
+    B = 4
+    x = torch.randn(B, 3, 16, 16, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    t_tensor = torch.full((B,), 300, dtype=torch.long)
+    a_hat = torch.cumprod(1 - torch.linspace(1e-4, 0.02, 1000), 0)[30]
+    out = {}
+    for wrt in ("input", "score"):
+        pipe = gg.DiffusionClassConditionalGuidedGradient(model, None, 0.9, 16, torch.device("cpu"), B, 0, M=4, gradient_wrt=wrt,
+                                                          lambda_update=0.1)
+        with torch.no_grad():
+            eps = model(x, t_tensor, y=y)[:, :3].clone()
+        with seeded_noise(14), quiet():
+            u, upd = pipe.estimate_score_update(x.clone(), y, 7, t_tensor, eps, x.clone(), a_hat)
+        m = pd.calculate_threshold_map(0.9, None, u.detach(), "higher").float()
+        with torch.no_grad():
+            post = eps + 0.1 * upd
+            new = eps * (1 - m) + post * m
+        out.update({f"{wrt}_u": u.detach(), f"{wrt}_update": upd.detach(), f"{wrt}_mask": m, f"{wrt}_eps_new": new.detach()})
+    save("gradient_update", x=x, y=y, a_hat=a_hat, t=300, M=4, **out)
 
 
 def main():

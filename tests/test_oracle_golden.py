@@ -160,3 +160,29 @@ def test_sd_percentile_guidance_matches_reference(golden_dir):
     mask = O.calculate_threshold_map(0.9, None, u, "higher")
     out = O.posterior_blend(eps, u, mask, 5, a_hat, batch_sum=True)
     assert same(out.numpy(), g["post_out"])
+
+
+@pytest.mark.parametrize("wrt", ["input", "score"])
+def test_gradient_score_update_matches_reference(golden_dir, wrt):
+    """estimate_score_update of the guided-gradient pipeline + its blend lines, recorded from the unmodified reference"""
+    from tests.toy_models import ToyADMWithParameter
+    g = load(golden_dir, "gradient_update")
+    model = ToyADMWithParameter(3, seed=14).eval()
+    x, y = T(g["x"]), T(g["y"])
+    t_tensor = torch.full((x.shape[0],), int(g["t"]), dtype=torch.long)
+    a_hat = T(g["a_hat"])
+    predict = lambda inp: model(inp, t_tensor, y=y)[:, :3]   # noqa: E731
+    with torch.no_grad():
+        eps = predict(x).clone()
+    with seeded_noise(14):
+        u, upd = O.gradient_score_update(predict, x, eps, x, int(g["M"]), a_hat, wrt)
+    assert same(u.numpy(), g[f"{wrt}_u"]) and same(upd.numpy(), g[f"{wrt}_update"])
+    m = O.calculate_threshold_map(0.9, None, u, "higher")
+    assert same(m.numpy(), g[f"{wrt}_mask"])
+    assert same(O.gradient_blend_masked(eps, upd, m, 0.1).numpy(), g[f"{wrt}_eps_new"])
+
+
+def test_pixel_threshold_restatement_matches_reference_script(golden_dir):
+    g = load(golden_dir, "pixel_thresholds")
+    for perc in (0.15, 0.9):
+        assert same(O.fit_pixel_thresholds(T(g["unc"]), perc).numpy(), g[f"thr_{perc}"])

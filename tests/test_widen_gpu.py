@@ -149,3 +149,72 @@ def test_guided_step_gradient_forms_with_unguided_x0(ops, form):
         x0 = x0.clamp(-1, 1)
     prev = c.sqrt_alpha_prev * x0 + c.dir_coef * e2
     assert bits_equal(r["eps"], e2) and bits_equal(r["x0"], x0) and bits_equal(r["prev"], prev)
+
+
+# ------------------------------------------------------------------------------------------- the guided pipelines' pieces
+@pytest.mark.parametrize("wrt", ["input", "score"])
+def test_guided_gradient_pipeline_score_update(ops, golden_dir, wrt):
+    """DiffusionClassConditionalGuidedGradient.estimate_score_update + blend against the fixture recorded from the reference
+    class (gradients: fp32 tolerance, the reduction's backward runs in du_moments_backward)"""
+    from diffusion_uncertainty_b200.pipeline_uncertainty.pipeline_sampler_class_conditional_uncertainty_guided_gradient import (
+        DiffusionClassConditionalGuidedGradient, guided_gradient_blend)
+    from tests.toy_models import ToyADMWithParameter, seeded_noise
+    g = {k: v for k, v in np.load(os.path.join(golden_dir, "gradient_update.npz")).items()}
+    model = ToyADMWithParameter(3, seed=14).eval().to(dev())
+    x, y = torch.from_numpy(g["x"]).to(dev()), torch.from_numpy(g["y"]).to(dev())
+    t_tensor = torch.full((x.shape[0],), int(g["t"]), dtype=torch.long, device=dev())
+    a_hat = torch.from_numpy(g["a_hat"])
+    pipe = DiffusionClassConditionalGuidedGradient(model, None, 0.9, 16, dev(), x.shape[0], 0, M=int(g["M"]), gradient_wrt=wrt,
+                                                   lambda_update=0.1)
+    with torch.no_grad():
+        eps = model(x, t_tensor, y=y)[:, :3].clone()
+    with seeded_noise(14):
+        u, upd = pipe.estimate_score_update(x.clone(), y, 7, t_tensor, eps, x.clone(), a_hat)
+    assert_close_rel(u, torch.from_numpy(g[f"{wrt}_u"]), 1e-5, atol=1e-12)
+    assert_close_rel(upd, torch.from_numpy(g[f"{wrt}_update"]), 1e-4, atol=1e-7)
+    # the blend is bit-exact given the recorded inputs
+    new = guided_gradient_blend(eps, torch.from_numpy(g[f"{wrt}_update"]).to(dev()), torch.from_numpy(g[f"{wrt}_mask"]).to(dev()), 0.1)
+    assert bits_equal(new, torch.from_numpy(g[f"{wrt}_eps_new"]))
+
+
+def test_second_order_blend(ops):
+    from diffusion_uncertainty_b200.pipeline_uncertainty.pipeline_sampler_class_conditional_uncertainty_guided_second_order import (
+        second_order_blend, second_order_momentum_update)
+    from tests.toy_models import seeded_noise
+    eps, scores, _ = synth(3, 3, 16, 3, seed=5)
+    u = O.centered_second_moment(scores, eps)
+    m = O.calculate_threshold_map(0.8, None, u, "higher")
+    with seeded_noise(5):
+        want = eps + u * torch.sign(torch.randn_like(eps)) * m      # second_order.py:249
+    with seeded_noise(5):
+        got = second_order_blend(eps.to(dev()), u.to(dev()), m.to(dev()))
+    assert bits_equal(got, want)
+    mom, corr, root = second_order_momentum_update(None, u.to(dev()), 3)
+    assert bits_equal(mom, u)
+    assert_close_rel(root, torch.sqrt(u / (1 - 0.99 ** 3 + 1e-5)), 1e-6)   # plain torch ops on either device
+
+
+def test_guided_gradient_pipeline_call(ops):
+    """the whole __call__ loop on the GPU: deterministic, uint8 images; with percentile 1.0 nothing exceeds the threshold, so
+    the guided run equals plain sampling with the same scheduler"""
+    from diffusion_uncertainty_b200.pipeline_uncertainty.pipeline_sampler_class_conditional_uncertainty_guided_gradient import \
+        DiffusionClassConditionalGuidedGradient
+    from diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim_flip import DDIMSchedulerUncertaintyImagenetClassConditioned
+    from tests.toy_models import ToyADMWithParameter, seeded_noise
+    model = ToyADMWithParameter(3, seed=3).eval().to(dev())
+    g = torch.Generator().manual_seed(3)
+    X_T, y = torch.randn(5, 3, 16, 16, generator=g), torch.randint(0, 10, (5,), generator=g)
+
+    def run(threshold, lam):
+        sched = DDIMSchedulerUncertaintyImagenetClassConditioned(unet=model, after_step=0, num_steps_uc=1)
+        sched.set_timesteps(10)
+        pipe = DiffusionClassConditionalGuidedGradient(model, sched, threshold, 16, dev(), 3, 0, M=3, lambda_update=lam)
+        with seeded_noise(30):
+            return pipe(X_T=X_T, y=y, start_step=4, num_steps=3)
+
+    a, b = run(0.9, 0.5), run(0.9, 0.5)
+    assert a["gen_images"].dtype == torch.uint8 and a["gen_images"].shape == (5, 3, 16, 16) and torch.equal(a["gen_images"], b["gen_images"])
+    assert torch.equal(a["x_t"], X_T) and torch.equal(a["y"], y)
+    off, plain = run(1.0, 0.5), run(0.9, 0.0)
+    assert torch.equal(off["gen_images"], plain["gen_images"])
+    assert not torch.equal(a["gen_images"], plain["gen_images"])

@@ -67,6 +67,19 @@ class ToyADM(torch.nn.Module):
         return h.clamp(-3.0, 3.0)
 
 
+class ToyADMWithParameter(ToyADM):
+    """ToyADM plus one trainable (zero) parameter in the graph, so that the output requires grad even when the input does not —
+    like a real score model; the reference's guided-gradient pipeline back-propagates the raw prediction first
+    (pipeline_sampler_class_conditional_uncertainty_guided_gradient.py:182-183)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.p = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, x, t, y=None, **kw):
+        return super().forward(x, t, y=y, **kw) + self.p * 0.0
+
+
 class ToySDUNet(torch.nn.Module):
     """diffusers-UNet2DConditionModel-shaped stand-in: called by keyword, returns a 1-tuple."""
 
