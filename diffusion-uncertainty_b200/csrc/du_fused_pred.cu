@@ -419,7 +419,11 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
     if (t == 384 || t == 512 || t == 768 || t == 1024) threads = t;
   }
   const int64_t trips = (ngroups + threads - 1) / threads;
-  if (trips < 4) return 0;    // a pilot of 1/trips of the slice has to be a small part of it
+  // The pilot (~4 us) and the latency-bound finish (~8 us) are fixed costs: below ~8 trips per thread the three-phase kernel
+  // is faster (ImageNet-64, b128: 17.4 us against 18.8 us), above it the single pass wins (ImageNet-128: 49.2 against 54.3).
+  const char* e_m = getenv("DU_FUSED_PRED_MIN_TRIPS");
+  const int64_t min_trips = (e_m && atoi(e_m) >= 4) ? atoi(e_m) : 8;
+  if (trips < min_trips) return 0;
   // pilot sample: trip 0 of every warp = row (warp * trips) of 32 groups
   int64_t pilot_groups = 0;
   for (int w = 0; w < threads / 32; ++w) {

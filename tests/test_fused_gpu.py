@@ -115,6 +115,7 @@ def test_fused_predictive_kernel_matches_oracle(ops, monkeypatch, pred, threads,
     if threads:
         env["DU_FUSED_PRED_THREADS"] = threads
     run_case(ops, 3, 3, 128, 5, 0.9, mode, batch_sum=batch_sum, higher=higher, seed=21, env=env, monkeypatch=monkeypatch)
+    env["DU_FUSED_PRED_MIN_TRIPS"] = 4    # 64x64 images have 6 trips per thread: below the default switch-over point
     run_case(ops, 5, 3, 64, 5, 0.9, mode, batch_sum=batch_sum, higher=higher, seed=22, env=env, monkeypatch=monkeypatch)
 
 
