@@ -95,6 +95,9 @@ PROTOTYPES = {
     "du_batch_sum": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, vp]),
     "du_perturb": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, f32, f32, i64, i64, vp, i64, C.c_int, vp]),
     "du_accumulate_slot": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, C.c_int, vp]),
+    "du_perturb_randn": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_uint64, vp, f32, f32, vp, C.c_int, vp, C.c_int, vp]),
+    "du_randn_offset_increment": (C.c_int, [i64, C.POINTER(C.c_uint64)]),
+    "du_rng_advance": (C.c_int, [vp, C.c_uint64, vp]),
     "du_image_uint8": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, vp]),
     "du_fused_uncertainty_step": (C.c_int, [C.POINTER(FusedParams), vp]),
     "du_fused_supported": (C.c_int, [i64, C.c_int]),

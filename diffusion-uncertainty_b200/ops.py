@@ -525,6 +525,115 @@ def perturb(x: torch.Tensor, noise: torch.Tensor, a: float, b: float, out_dtype:
     return out
 
 
+_TORCH_RANDN_LIKE = torch.randn_like     # the genuine function: a caller that replaced torch.randn_like keeps its replacement
+
+
+def randn_fusable(x: torch.Tensor, generator: Optional[torch.Generator] = None) -> bool:
+    """True when `torch.randn_like(x)` may be drawn inside the perturbation kernel with the identical result: a dense CUDA
+    tensor (torch's generator kernel then indexes elements linearly, the mapping du_perturb_randn reproduces), fewer than
+    2^31 elements, torch.randn_like not replaced by the caller, not inside a CUDA-graph capture (torch's generator keeps its
+    offset on the device there; use DeviceRng for captured draws)."""
+    return (x.is_cuda and x.dtype in _DT and x.is_contiguous() and 0 < x.numel() < 2 ** 31
+            and torch.randn_like is _TORCH_RANDN_LIKE and not torch.cuda.is_current_stream_capturing()
+            and (generator is None or generator.device.type == "cuda"))
+
+
+def randn_offset_increment(numel: int) -> int:
+    """Philox offset one `numel`-element normal draw consumes on the current device (du_randn_offset_increment)."""
+    inc = C.c_uint64(0)
+    L.check(L.load().du_randn_offset_increment(int(numel), C.byref(inc)))
+    return int(inc.value)
+
+
+def _claim_philox(x: torch.Tensor, generator: Optional[torch.Generator]):
+    """Take (seed, offset) for one draw of x.numel() normals from the torch generator of x's device and advance it exactly
+    as torch's own kernel launch would (CUDAGeneratorImpl::philox_cuda_state)."""
+    if generator is not None:
+        gen = generator
+    else:
+        torch.cuda.init()          # default_generators is empty until CUDA is initialised
+        gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(offset + randn_offset_increment(x.numel()))
+    return seed & 0xFFFFFFFFFFFFFFFF, offset
+
+
+def perturb_randn(x: torch.Tensor, a: float, b: float, generator: Optional[torch.Generator] = None, want_noise: bool = False,
+                  device_state: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None):
+    """a*x + b*n, n = what `torch.randn_like(x)` would return now (bit-identical, generator advanced the same way), drawn in
+    the kernel (du_perturb_randn): x read once, out written once, no noise tensor in HBM unless want_noise.
+    device_state: int64[2] CUDA tensor {seed, offset} for draws replayed from a CUDA graph (see DeviceRng)."""
+    if not (x.is_cuda and x.dtype in _DT and x.is_contiguous()):
+        raise RuntimeError("perturb_randn needs a dense CUDA tensor (no CPU fallback; use torch.randn_like + perturb for views)")
+    _stream_ptr = _stream(x)
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    noise = torch.empty_like(x) if want_noise else None
+    if device_state is not None:
+        seed, offset, st_ptr = 0, 0, C.c_void_p(device_state.data_ptr())
+    else:
+        (seed, offset), st_ptr = _claim_philox(x, generator), None
+    rc = L.load().du_perturb_randn(C.c_void_p(x.data_ptr()), _DT[x.dtype], x.numel(), seed, offset, st_ptr, float(a), float(b),
+                                   C.c_void_p(out.data_ptr()), _DT[out.dtype],
+                                   C.c_void_p(noise.data_ptr()) if want_noise else None, _DT[x.dtype], _stream_ptr)
+    L.check(rc)
+    _count()
+    return (out, noise) if want_noise else out
+
+
+def randn_like(x: torch.Tensor, generator: Optional[torch.Generator] = None, device_state: Optional[torch.Tensor] = None):
+    """`torch.randn_like(x)` from du_perturb_randn's generator path alone (used by the tests and by DeviceRng)."""
+    if not (x.is_cuda and x.dtype in _DT):
+        raise RuntimeError("randn_like needs a CUDA tensor")
+    out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    if x.numel() == 0:
+        return out
+    _stream_ptr = _stream(x)
+    if device_state is not None:
+        seed, offset, st_ptr = 0, 0, C.c_void_p(device_state.data_ptr())
+    else:
+        (seed, offset), st_ptr = _claim_philox(out, generator), None
+    L.check(L.load().du_perturb_randn(None, _DT[x.dtype], out.numel(), seed, offset, st_ptr, 0.0, 0.0, None, _DT[x.dtype],
+                                      C.c_void_p(out.data_ptr()), _DT[x.dtype], _stream_ptr))
+    _count()
+    return out
+
+
+def perturb_fresh(x: torch.Tensor, a: float, b: float, noise_like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`a*x + b*torch.randn_like(noise_like or x)`: ONE launch with the noise drawn in registers when torch's draw can be
+    reproduced in the kernel (randn_fusable), else torch.randn_like followed by du_perturb.  Same values, same generator
+    state afterwards, either way."""
+    like = x if noise_like is None else noise_like
+    if like.shape == x.shape and like.dtype == x.dtype and like.device == x.device and randn_fusable(x):
+        return perturb_randn(x, a, b)
+    noise = torch.randn_like(like)
+    return perturb(x, noise if noise.shape == x.shape else noise.expand(x.shape), a, b)
+
+
+class DeviceRng:
+    """A Philox {seed, offset} pair in device memory, for perturbation draws inside a captured CUDA graph: every replay
+    continues the stream (du_rng_advance is part of the graph), and the values equal torch's for the same (seed, offset)."""
+
+    def __init__(self, device, seed: int, offset: int = 0):
+        self.state = torch.tensor([seed, offset], dtype=torch.int64, device=device)
+
+    def perturb(self, x: torch.Tensor, a: float, b: float, want_noise: bool = False):
+        r = perturb_randn(x, a, b, device_state=self.state, want_noise=want_noise)
+        self.advance(x.numel(), x)
+        return r
+
+    def randn_like(self, x: torch.Tensor):
+        r = randn_like(x, device_state=self.state)
+        self.advance(x.numel(), x)
+        return r
+
+    def advance(self, numel: int, like: torch.Tensor):
+        L.check(L.load().du_rng_advance(C.c_void_p(self.state.data_ptr()), randn_offset_increment(numel), _stream(like)))
+        _count()
+
+    def offset(self) -> int:
+        return int(self.state[1].item())
+
+
 def accumulate_slot(src: torch.Tensor, dst_slot: torch.Tensor):
     """Copy/convert one step's map into its slot view buffer[:, t] (du_accumulate_slot)."""
     s, d = Rows(src, "src"), Rows(dst_slot, "dst")

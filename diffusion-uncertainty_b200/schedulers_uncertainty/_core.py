@@ -288,25 +288,23 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
             return None
         return self.map_sink.next_slot(like.shape, dtype)
 
-    def _perturbed_input(self, st: StepState, base_x0: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    def _perturbed_input(self, st: StepState, base_x0: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """F7: the model input of one perturbed forward.  predict_next: sqrt(1-beta_t) x_{t-1} + sqrt(beta_t) n
-        (…zigzag_centered.py:538); else add_noise(x0, n, t) (:535, 593-626).  One launch (du_perturb)."""
+        (…zigzag_centered.py:538); else add_noise(x0, n, t) (:535, 593-626).  One launch: with noise=None the draw
+        `n = torch.randn_like(pred_x_0)` (:529) happens inside it (du_perturb_randn, torch's Philox stream bit for bit)."""
         t = st.t
         if self.predict_next:
             a, b = float(torch.sqrt(1 - self.betas[t])), float(torch.sqrt(self.betas[t]))
-            x_hat = ops.perturb(st.prev, noise, a, b)
+            base = st.prev
         else:
             a, b = float(self.alphas_cumprod[t] ** 0.5), float((1 - self.alphas_cumprod[t]) ** 0.5)
-            x_hat = ops.perturb(base_x0, noise, a, b)
+            base = base_x0
+        x_hat = ops.perturb_fresh(base, a, b, noise_like=st.x0) if noise is None else ops.perturb(base, noise, a, b)
         return self.scale_model_input(x_hat, t)
 
     def _perturbed_scores(self, st: StepState) -> List[torch.Tensor]:
         """M forwards on independently re-noised inputs (…uncertainty_centered.py:522-538)."""
-        scores = []
-        for _ in range(self.M):
-            noise = torch.randn_like(st.x0)
-            scores.append(self.predict_model(self._perturbed_input(st, st.x0, noise), st.t))
-        return scores
+        return [self.predict_model(self._perturbed_input(st, st.x0), st.t) for _ in range(self.M)]
 
     def _reduce(self, scores: List[torch.Tensor], mode: str, center: Optional[torch.Tensor] = None,
                 out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:

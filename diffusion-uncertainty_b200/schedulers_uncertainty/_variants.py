@@ -40,12 +40,11 @@ class ZigZagCentered(UncertaintyDDIMCore):
             x_t1 = st.x0   # the reference clones; nothing here writes in place
             out = None
             for j in range(self.num_zigzag):
-                noise = torch.randn_like(st.x0)
                 if self.predict_next:
                     a, b = float(torch.sqrt(1 - self.betas[st.t])), float(torch.sqrt(self.betas[st.t]))
-                    x_hat = ops.perturb(self._chain_base(st, x_t1), noise, a, b)
+                    x_hat = ops.perturb_fresh(self._chain_base(st, x_t1), a, b, noise_like=st.x0)   # noise drawn in the kernel
                 else:
-                    x_hat = self.add_noise(x_t1, noise, st.t)
+                    x_hat = self.add_noise(x_t1, torch.randn_like(st.x0), st.t)
                 x_hat = self.scale_model_input(x_hat, st.t)
                 out = self.predict_model(x_hat, st.t)
                 if j != self.num_zigzag - 1 and chain_used:
@@ -91,8 +90,7 @@ class UncertaintyImage(UncertaintyDDIMCore):
         c = ops.make_coeffs(h["sqrt_alpha_t"], h["sqrt_beta_t"], h["sqrt_alpha_prev"], h["dir_coef"], clip_sample=False)
         cands = []
         for _ in range(self.M):
-            noise = torch.randn_like(st.x0)
-            x_hat = self._perturbed_input(st, st.x0, noise)
+            x_hat = self._perturbed_input(st, st.x0)
             out = self.predict_model(x_hat, st.t)
             cands.append(ops.ddim_step(out, x_hat, c, want_prev=True, want_x0=False)[0])
         return self._reduce(cands, "var")
@@ -126,8 +124,7 @@ class CenteredD(UncertaintyDDIMCore):
         x_next = ops.ddim_step(st.eps, st.sample, c, want_prev=False, want_x0=True)[1]
         scores = []
         for _ in range(self.M):
-            noise = torch.randn_like(st.x0)
-            scores.append(self.predict_model(ops.perturb(x_next, noise, sa, sb), ending_step))
+            scores.append(self.predict_model(ops.perturb_fresh(x_next, sa, sb, noise_like=st.x0), ending_step))
         return self._reduce(scores, "centered", center=st.eps)
 
 

@@ -87,8 +87,7 @@ def get_uncertainty_guided_score_with_percentile(pred_epsilon: Tensor, input: Te
             x0 = ops.ddim_step(_rows_like(pred_epsilon, input), input, c_x0, want_prev=False, want_x0=True)[1]
             preds = []
             for _ in range(M):
-                noise = torch.randn_like(pred_epsilon)
-                x_hat = ops.perturb(x0, _rows_like(noise, x0), sa, sb)
+                x_hat = ops.perturb_fresh(x0, sa, sb, noise_like=pred_epsilon)     # `torch.randn_like(pred_epsilon)` drawn in the kernel
                 out, t_tensor = _forward(model, model_type, x_hat, t_tensor, y, guidance_scale, extra_diffusion_kwargs)
                 preds.append(out)
             u = ops.moments(preds, center=pred_epsilon, mode="var_with_center", out_dtype=preds[0].dtype)

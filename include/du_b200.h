@@ -225,6 +225,27 @@ int du_perturb(const void* x, int64_t x_stride, int x_dtype, const void* noise, 
                int out_dtype, du_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * F7 + N1 — the same combination with the noise drawn in the kernel:
+ *   n   = the N standard normals `torch.randn_like(x)` yields on a CUDA device for the Philox generator state
+ *         (seed, offset) — bit-identical (same Philox4x32-10 words, same Box-Muller, same element mapping as
+ *         ATen/native/cuda/DistributionTemplates.h `normal_and_transform`), rounded to noise_dtype;
+ *   out = a*x + b*n (one rounding per operation, as du_perturb).
+ * x: N contiguous elements (NULL: only the noise is produced, into noise_out).  noise_out: nullable.
+ * device_state: nullable device pointer to {seed, offset}; when given it overrides the host pair (draws that replay
+ * from a CUDA graph: advance it in the same graph with du_rng_advance).
+ * Replaces `noise = torch.randn_like(pred_x_0)` + the expression of
+ * SU/scheduling_ddim_uncertainty_zigzag_centered.py:529-538, SU/scheduling_ddim_uncertainty_centered.py:525-531,
+ * uncertainty_guidance.py:86-88.  The caller advances its generator by du_randn_offset_increment(N).
+ * ---------------------------------------------------------------------------------------------- */
+int du_perturb_randn(const void* x, int x_dtype, int64_t N, uint64_t seed, uint64_t offset,
+                     const uint64_t* device_state, float a, float b, void* out, int out_dtype,
+                     void* noise_out, int noise_dtype, du_stream_t stream);
+/* Philox offset consumed by one N-element normal draw on the current device (torch's calc_execution_policy). */
+int du_randn_offset_increment(int64_t N, uint64_t* increment_out);
+/* device_state[1] += increment, on the stream (graph-capturable). */
+int du_rng_advance(uint64_t* device_state, uint64_t increment, du_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * F8 — copy (and convert) one step's map into its slot of the [B, T_uc, ...] accumulation buffer:
  * dst row b = dst + b*dst_stride.  generate_samples.py:192-201,229-231.
  * ---------------------------------------------------------------------------------------------- */
