@@ -115,14 +115,15 @@ class ClockSampler:
             except Exception:
                 pass
 
-    def summary(self):
+    def summary(self, window=None):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm), "window": "sustained replays of the timed graph around the K timed steps (the K-step region "
-                                              "is shorter than one nvidia-smi sampling period)"}
+                "samples": len(sm),
+                "window": window or "sustained replays of the timed graph around the K timed steps (the K-step region is shorter "
+                                    "than one nvidia-smi sampling period)"}
 
 
 # ------------------------------------------------------------------------------------------- CPU arms
@@ -233,11 +234,13 @@ def run_ours(args):
 
     def step(i):
         slot = maps[:, i % T_UC]
-        if args.batch_sum:
-            ops.batch_sum(eps, out=S_buf)            # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
         if fused:
             plan.set_map_out(slot)
+            if args.batch_sum:                       # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
+                return plan.launch_with_batch_sum(eps, S_buf)["prev"]      # du_batch_sum, then the step as its dependent launch
             return plan.launch()["prev"]
+        if args.batch_sum:
+            ops.batch_sum(eps, out=S_buf)
         u = ops.moments(scores, center=eps, mode="var_with_center", out=slot)
         thr = ops.quantile_threshold(u, q)
         r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=S_buf if args.batch_sum else eps,
@@ -397,13 +400,129 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- sampling-loop arm
+LOOPS = {
+    # name: (feeder factory, total batch, C, H, betas, scheduler kwargs, generation steps)
+    "imagenet128_adm_loop": ("adm_imagenet128", 128, 3, 128, dict(beta_start=1e-4, beta_end=0.02, beta_schedule="linear"),
+                             dict(M=5, after_step=40, num_steps_uc=10, num_zigzag=3), 50),
+}
+
+
+def run_loop(args):
+    """BASELINE.json metric (iii): ImageNet-128 M=5 img/s over the FULL sampling loop of the README command
+    (scripts/generate_dataset_score_uncertainty_imagenet.py: 50 DDIM steps, uncertainty window = the last 10, M=5 x num_zigzag=3
+    perturbed forwards per window step, maps accumulated and copied to the host), through the drop-in
+    `generate_samples_model_scheduler_class_conditioned_from_tensor` with the zigzag-centred scheduler, under torch.autocast as
+    the reference runs it.  The score model is a random-init ADM-128-shaped feeder (tools/adm_feeder.py).  The batch of 128 is
+    SHARDED over the ranks (strong scaling, no collective) — the reference's mp.spawn slicing.  One step = one whole loop."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import adm_feeder
+    from diffusion_uncertainty_b200 import ops
+    from diffusion_uncertainty_b200.generate_samples import generate_samples_model_scheduler_class_conditioned_from_tensor as gen_loop
+    from diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim_uncertainty_zigzag_centered import \
+        DDIMSchedulerUncertaintyImagenetClassConditioned as Sched
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the uncertainty path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    factory, B_total, C, H, betas, skw, n_steps = LOOPS[args.workload]
+    B = B_total // world
+    model = getattr(adm_feeder, factory)().to(dev).eval()
+    sched = Sched.from_config(dict(num_train_timesteps=1000, clip_sample=True, set_alpha_to_one=True, steps_offset=0,
+                                   prediction_type="epsilon", timestep_spacing="leading", **betas), unet=model, **skw)
+    sched.set_timesteps(n_steps)
+    g = torch.Generator().manual_seed(49394 + rank)
+    X_T = torch.randn(B, C, H, H, generator=g).pin_memory()
+    y = torch.randint(0, 1000, (B,), generator=g)
+    torch.manual_seed(1234 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_loop():
+        with torch.autocast("cuda"):
+            return gen_loop(X_T, y, B, dev, model, sched)
+
+    warm = max(1, min(args.warmup, 1)) if args.loop_warmup is None else args.loop_warmup
+    for _ in range(warm):
+        res = one_loop()
+    barrier()
+    steps = args.loop_steps
+    launches0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            res = one_loop()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+    ms = max(e0.elapsed_time(e1), wall * 1e3)     # the loop ends with host-side waits on the pinned copies: wall covers them
+    launches = ops.launch_count - launches0
+    # the share of the score model: one forward of the same batch, timed alone
+    t_tensor = torch.full((B,), 180, device=dev, dtype=torch.long)
+    xg, yg = X_T.to(dev), y.to(dev)
+    with torch.no_grad(), torch.autocast("cuda"):
+        for _ in range(2):
+            model(xg, t_tensor, y=yg)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(5):
+            model(xg, t_tensor, y=yg)
+        f1.record()
+    torch.cuda.synchronize()
+    fwd_ms = f0.elapsed_time(f1) / 5
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    n_fwd = n_steps + skw["num_steps_uc"] * skw["M"] * skw["num_zigzag"]
+    if rank == 0:
+        ms_per_loop = ms / steps
+        unc = res["uncertainty"]
+        line = {
+            "metric": "imagenet128_m5_sampling_loop_throughput", "value": B_total / (ms_per_loop * 1e-3), "unit": "img/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_loop, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16 autocast (model) / f32 (uncertainty path)", "data": "synthetic",
+            "config": {"workload": args.workload, "global_batch": B_total, "batch_per_gpu": B, "generation_steps": n_steps,
+                       "start_step_uc": skw["after_step"], "num_steps_uc": skw["num_steps_uc"], "M": skw["M"],
+                       "num_zigzag": skw["num_zigzag"], "scheduler": "uncertainty_zigzag_centered",
+                       "model": "random-init ADM-128-shaped feeder (tools/adm_feeder.py, 421.5 M parameters)",
+                       "parallelism": f"batch-sharded x{world}, no collective", "step": "one full sampling loop of the batch"},
+            "model_forwards_per_loop": n_fwd, "model_forward_ms": fwd_ms,
+            "model_share_of_loop": n_fwd * fwd_ms / ms_per_loop,
+            "non_model_ms_per_loop": ms_per_loop - n_fwd * fwd_ms,
+            "e2e": {"value": B_total / (ms_per_loop * 1e-3), "unit": "img/s", "h2d_bytes_per_step": X_T.numel() * 4 * world,
+                    "d2h_bytes_per_step": (2 * unc.numel() * unc.element_size() + res["gen_images"].numel()) * world,
+                    "note": "the loop itself is end to end: X_T comes from pinned host memory, maps / scores / uint8 images end in host memory"},
+            "gpu_launches": launches, "map_shape": list(unc.shape), "map_finite": bool(torch.isfinite(unc).all()),
+            "clocks": clocks.summary("the timed loops"),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="imagenet128_adm_b128_m5", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="imagenet128_adm_b128_m5", choices=list(WORKLOADS) + list(LOOPS))
+    ap.add_argument("--loop-steps", type=int, default=1, help="sampling-loop workloads: timed loops (one loop = one step)")
+    ap.add_argument("--loop-warmup", type=int, default=None, help="sampling-loop workloads: untimed warm-up loops (default 1)")
     ap.add_argument("--dtype", default="fp32", choices=list(DTYPES))
     ap.add_argument("--batch-sum", type=int, default=1, help="1 = reference behaviour (posterior sum over the batch axis)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -412,7 +531,14 @@ def main():
     ap.add_argument("--eager", action="store_true", help="time K eager launches from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.workload in LOOPS:
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the sampling loop needs the score model on a GPU; the reference "
+                                  "CPU arm exists for the uncertainty-step workloads only"}))
+            return
+        run_loop(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

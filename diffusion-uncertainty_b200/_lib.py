@@ -65,7 +65,7 @@ class FusedParams(C.Structure):
         ("B", i64), ("n", i64),
         ("unc_out", vp), ("unc_stride", i64),
         ("thr_out", vp),
-        ("prev_out", vp), ("prev_stride", i64), ("prev_dtype", i32), ("_pad0", i32),
+        ("prev_out", vp), ("prev_stride", i64), ("prev_dtype", i32), ("S_overlap", i32),
         ("x0_out", vp), ("x0_stride", i64),
         ("eps_out", vp), ("eps_out_stride", i64),
         ("mask_out", vp), ("mask_out_stride", i64),
@@ -95,6 +95,8 @@ PROTOTYPES = {
     "du_batch_sum": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, vp]),
     "du_perturb": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, f32, f32, i64, i64, vp, i64, C.c_int, vp]),
     "du_accumulate_slot": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, C.c_int, vp]),
+    "du_dpm_solver_update": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, vp, i64, C.c_int, f32, f32, f32, f32, i64, i64, vp, i64,
+                                       C.c_int, vp]),
     "du_perturb_randn": (C.c_int, [vp, C.c_int, i64, C.c_uint64, C.c_uint64, vp, f32, f32, vp, C.c_int, vp, C.c_int, vp]),
     "du_randn_offset_increment": (C.c_int, [i64, C.POINTER(C.c_uint64)]),
     "du_rng_advance": (C.c_int, [vp, C.c_uint64, vp]),

@@ -30,6 +30,7 @@ struct PredKParams {
   uint32_t open_low, open_high;  // band is open at that end (rank window touched the ends of the pilot sample)
   uint32_t cand_max;    // capacity of the candidate list (entries)
   uint32_t prefetch_rows;  // rows per warp pulled into L2 while the pilot runs
+  uint64_t pol_stream;     // L2 eviction policy of the once-read streams (scores, sample, eps on its last read)
 };
 
 // misc words used only here: [44] candidate count, [45] list overflow, [46] LB bin, [47] UB bin
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   const int trips = (int)pk.trips;
   uint32_t nan_seen = 0;
   uint32_t LB = 0, UB = 0;   // band in key space, known after the pilot
+  const uint64_t pol = pk.pol_stream;
 
   // one group of VEC elements: map value (from the scores, or replayed from the slot), histogram, mask by band, update
   auto do_group = [&](int g, bool valid, bool from_scores, bool pilot_only) {
@@ -106,12 +108,14 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
     const uint32_t g_elems = (uint32_t)g * VEC;
     if (valid) {
       const uint32_t byte_off = g_elems * (uint32_t)sizeof(T);
-      const uint4 raw_e = ldg_stream_128_at(eps_row, byte_off);
+      // eps was just read by du_batch_sum (evict-last): it comes from L2.  The pilot reads its rows once more later (normal
+      // priority); every other read is the last one and, like the scores and the sample, asks to be evicted first.
+      const uint4 raw_e = ldg_stream_128_pol(reinterpret_cast<const char*>(eps_row) + byte_off, pilot_only ? kL2EvictNormal : pol);
       uint4 raw_s[VEC / 4];
       float4 raw_S[VEC / 4];
       if (!pilot_only) {
 #pragma unroll
-        for (int h = 0; h < VEC / 4; ++h) raw_s[h] = ldg_stream_128(xs + g_elems + 4 * h);
+        for (int h = 0; h < VEC / 4; ++h) raw_s[h] = ldg_stream_128_pol(xs + g_elems + 4 * h, pol);
         if (Srow) {
 #pragma unroll
           for (int h = 0; h < VEC / 4; ++h) raw_S[h] = __ldg(reinterpret_cast<const float4*>(Srow + g_elems + 4 * h));
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       }
       if (from_scores) {
         float c[VEC], k[VEC], s1[VEC], s2[VEC];
-        if constexpr (MT > 0) accumulate_scores_ct<T, MT>(p.scores, srow, byte_off, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2);
+        if constexpr (MT > 0) accumulate_scores_ct<T, MT, true>(p.scores, srow, byte_off, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2, pol);
         else accumulate_scores<T>(p.scores, p.M, srow + g_elems, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2);
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
@@ -235,6 +239,9 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   stamp(kp, 1);
 
   // ---------------------------------------------------------------- stream: every other trip, then the pilot replayed
+  // Launched as the programmatic dependent of the du_batch_sum that produces S (S_overlap): everything above ran while that
+  // kernel was still summing; its result is complete and visible from here on.  A no-op for an ordinary launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int j = 1; j < trips; ++j) {
     const int g = group_of(j);
     do_group(g, g < ngroups, true, false);
@@ -362,13 +369,21 @@ static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t sm
   cfg.blockDim = dim3((unsigned)THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)plan.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pk.k.p.S && pk.k.p.S_overlap) {   // programmatic dependent of the preceding du_batch_sum (DU_FUSED_PDL=0 disables)
+    const char* e_pdl = getenv("DU_FUSED_PDL");
+    if (!(e_pdl && atoi(e_pdl) == 0)) {
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.numAttrs = 2;
+    }
+  }
   DU_CUDA(cudaLaunchKernelEx(&cfg, kern, pk));
   return 1;
 }
@@ -466,6 +481,11 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
   {
     const char* e_r = getenv("DU_FUSED_PREFETCH_ROWS");
     pk.prefetch_rows = e_r ? (uint32_t)atoi(e_r) : 0u;   // measured: the extra traffic delays the pilot more than it saves
+  }
+  {
+    // DU_L2_HINTS=0: every load at normal priority (A/B of the eviction hints)
+    const char* e_h = getenv("DU_L2_HINTS");
+    pk.pol_stream = (e_h && atoi(e_h) == 0) ? kL2EvictNormal : kL2EvictFirst;
   }
   const size_t smem = kPredFixedBytes + (size_t)cap * 16;
   switch (p.score_dtype) {

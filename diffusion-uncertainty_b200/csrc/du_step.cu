@@ -243,10 +243,13 @@ constexpr int BS_SPLIT = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(32 * BS_SPLIT) batch_sum_rows_kernel(const T* __restrict__ x, int64_t stride, int64_t B, int64_t n,
-                                                                       float* __restrict__ out) {
+                                                                       float* __restrict__ out, uint64_t pol) {
   using V = Vec16<T>;
   constexpr int VEC = V::VEC;
   __shared__ double part[BS_SPLIT][32][VEC];
+  // a fused step launched as this kernel's programmatic dependent (du_fused_params::S_overlap) may start its S-independent
+  // pilot now; it orders its first read of `out` with griddepcontrol.wait.  No effect for ordinary successors.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
   const int64_t per = (B + BS_SPLIT - 1) / BS_SPLIT;
   const int64_t b0 = r * per, b1 = (b0 + per < B) ? b0 + per : B;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(32 * BS_SPLIT) batch_sum_rows_kernel(const T* 
     for (; b + 8 <= b1; b += 8) {
       uint4 raw[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) raw[j] = ldg_stream_128(col + (b + j) * stride);
+      for (int j = 0; j < 8; ++j) raw[j] = ldg_stream_128_pol(col + (b + j) * stride, pol);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v[VEC];
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(32 * BS_SPLIT) batch_sum_rows_kernel(const T* 
     }
     for (; b < b1; ++b) {
       float v[VEC];
-      V::unpack(ldg_stream_128(col + b * stride), v);
+      V::unpack(ldg_stream_128_pol(col + b * stride, pol), v);
 #pragma unroll
       for (int e = 0; e < VEC; ++e) acc[e] += (double)v[e];
     }
@@ -487,9 +490,12 @@ extern "C" int du_batch_sum(const void* x, int64_t x_stride, int x_dtype, int64_
   if (B >= 2 * BS_SPLIT && n % vec == 0 && aligned(x, 16) && x_stride % vec == 0 && aligned(out, 16)) {
     const unsigned grid = (unsigned)((n / vec + 31) / 32);
     cudaStream_t st = (cudaStream_t)stream;
-    if (x_dtype == DU_F32) batch_sum_rows_kernel<float><<<grid, 32 * BS_SPLIT, 0, st>>>((const float*)x, x_stride, B, n, out);
-    else if (x_dtype == DU_F16) batch_sum_rows_kernel<__half><<<grid, 32 * BS_SPLIT, 0, st>>>((const __half*)x, x_stride, B, n, out);
-    else batch_sum_rows_kernel<__nv_bfloat16><<<grid, 32 * BS_SPLIT, 0, st>>>((const __nv_bfloat16*)x, x_stride, B, n, out);
+    // x (the step's eps) is read again by the kernel that consumes the sum: ask L2 to keep it (DU_L2_HINTS=0: normal priority)
+    const char* e_h = getenv("DU_L2_HINTS");
+    const uint64_t pol = (e_h && atoi(e_h) == 0) ? kL2EvictNormal : kL2EvictLast;
+    if (x_dtype == DU_F32) batch_sum_rows_kernel<float><<<grid, 32 * BS_SPLIT, 0, st>>>((const float*)x, x_stride, B, n, out, pol);
+    else if (x_dtype == DU_F16) batch_sum_rows_kernel<__half><<<grid, 32 * BS_SPLIT, 0, st>>>((const __half*)x, x_stride, B, n, out, pol);
+    else batch_sum_rows_kernel<__nv_bfloat16><<<grid, 32 * BS_SPLIT, 0, st>>>((const __nv_bfloat16*)x, x_stride, B, n, out, pol);
     DU_LAUNCH_CHECK("batch_sum_rows_kernel");
     return DU_OK;
   }

@@ -205,6 +205,30 @@ struct SlotSumF {
   }
 };
 
+// DPM-Solver multistep update (first / second order): out = (a*s + b*m0) + c*(k*(m0 - m1)), one rounding per operation in
+// the order the reference's Python expression evaluates (subtractions folded into the signs of b and c: x - y == x + (-y)
+// bit for bit).  m1 == nullptr: first order.
+struct DpmUpdateF {
+  const void* s; int64_t s_stride; int s_dtype;
+  const void* m0; int64_t m0_stride; int m0_dtype;
+  const void* m1; int64_t m1_stride; int m1_dtype;
+  float a, b_, c, k;
+  void* out; int64_t out_stride; int out_dtype;
+  template <int VEC> __device__ __forceinline__ void run(int64_t b, int64_t i) const {
+    float sv[VEC], v0[VEC], v1[VEC], o[VEC];
+    loadv<VEC>(s, b * s_stride + i, s_dtype, sv);
+    loadv<VEC>(m0, b * m0_stride + i, m0_dtype, v0);
+    if (m1) loadv<VEC>(m1, b * m1_stride + i, m1_dtype, v1);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      float t = __fadd_rn(__fmul_rn(a, sv[e]), __fmul_rn(b_, v0[e]));
+      if (m1) t = __fadd_rn(t, __fmul_rn(c, __fmul_rn(k, __fsub_rn(v0[e], v1[e]))));
+      o[e] = t;
+    }
+    storev<VEC>(out, b * out_stride + i, out_dtype, o);
+  }
+};
+
 static bool view_ok(const void* p, int dt) { return p != nullptr && dtype_ok(dt); }
 
 }  // namespace du
@@ -288,5 +312,16 @@ extern "C" int du_slot_sum(const void* x, int64_t x_stride, int64_t slot_stride,
   if (!view_ok(x, x_dtype) || !out || B < 0 || n < 0 || T < 0) return set_error(DU_ERR_BAD_ARG, "du_slot_sum: bad arguments");
   SlotSumF f{x, x_stride, slot_stride, x_dtype, T, out, out_stride};
   const bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && (slot_stride % 4 == 0) && vec4_ok(out, out_stride, DU_F32);
+  return launch_rows(B, n, vec, f, (cudaStream_t)stream);
+}
+
+extern "C" int du_dpm_solver_update(const void* sample, int64_t s_stride, int s_dtype, const void* m0, int64_t m0_stride, int m0_dtype,
+                                    const void* m1, int64_t m1_stride, int m1_dtype, float a, float b, float c, float k,
+                                    int64_t B, int64_t n, void* out, int64_t out_stride, int out_dtype, du_stream_t stream) {
+  if (!view_ok(sample, s_dtype) || !view_ok(m0, m0_dtype) || (m1 && !dtype_ok(m1_dtype)) || !view_ok(out, out_dtype) || B < 0 || n < 0)
+    return set_error(DU_ERR_BAD_ARG, "du_dpm_solver_update: bad arguments");
+  DpmUpdateF f{sample, s_stride, s_dtype, m0, m0_stride, m0_dtype, m1, m1_stride, m1_dtype, a, b, c, k, out, out_stride, out_dtype};
+  const bool vec = (n % 4 == 0) && vec4_ok(sample, s_stride, s_dtype) && vec4_ok(m0, m0_stride, m0_dtype) &&
+                   (!m1 || vec4_ok(m1, m1_stride, m1_dtype)) && vec4_ok(out, out_stride, out_dtype);
   return launch_rows(B, n, vec, f, (cudaStream_t)stream);
 }

@@ -525,6 +525,25 @@ def perturb(x: torch.Tensor, noise: torch.Tensor, a: float, b: float, out_dtype:
     return out
 
 
+def dpm_solver_update(sample: torch.Tensor, m0: torch.Tensor, m1: Optional[torch.Tensor], a: float, b: float, c: float = 0.0,
+                      k: float = 0.0) -> torch.Tensor:
+    """(a*sample + b*m0) + c*(k*(m0 - m1)) in one launch (du_dpm_solver_update); m1 None: a*sample + b*m0."""
+    sr, r0 = Rows(sample, "sample"), Rows(m0, "m0")
+    _same_rows(sr, r0, "dpm_solver_update")
+    r1 = None
+    if m1 is not None:
+        r1 = Rows(m1, "m1")
+        _same_rows(sr, r1, "dpm_solver_update")
+    dt = torch.promote_types(sample.dtype, m0.dtype)
+    out = torch.empty(sample.shape, device=sample.device, dtype=dt)
+    rc = L.load().du_dpm_solver_update(sr.ptr, sr.stride, sr.dt, r0.ptr, r0.stride, r0.dt, r1.ptr if r1 else None,
+                                       r1.stride if r1 else 0, r1.dt if r1 else L.F32, float(a), float(b), float(c), float(k),
+                                       sr.B, sr.n, C.c_void_p(out.data_ptr()), sr.n, _DT[dt], _stream(sample))
+    L.check(rc)
+    _count()
+    return out
+
+
 _TORCH_RANDN_LIKE = torch.randn_like     # the genuine function: a caller that replaced torch.randn_like keeps its replacement
 
 
@@ -754,6 +773,19 @@ class FusedStep:
         L.check(self._fn(self._ref, _stream(self._dev_tensor)))
         _count()
         return self.res
+
+    def launch_with_batch_sum(self, eps: torch.Tensor, S_out: torch.Tensor):
+        """The reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:116-119) followed by the step that consumes it, as
+        two back-to-back launches on one stream: du_batch_sum -> du_fused_uncertainty_step with S_overlap set, so the step
+        starts as the sum's programmatic dependent and its S-independent pilot overlaps the sum.  S_out: fp32 [C,H,W] row."""
+        batch_sum(eps, out=S_out)
+        if self.P.S != S_out.data_ptr() or not self.P.S_broadcast:
+            self.set_S(S_out, True)
+        self.P.S_overlap = 1
+        try:
+            return self.launch()
+        finally:
+            self.P.S_overlap = 0
 
 
 def fused_uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,

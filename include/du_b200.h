@@ -276,7 +276,12 @@ typedef struct du_fused_params {
   int64_t B, n;
   float* unc_out;       int64_t unc_stride;     /* map (or its accumulation slot)                    */
   float* thr_out;                               /* [B], nullable                                     */
-  void* prev_out;       int64_t prev_stride;    int32_t prev_dtype;   int32_t _pad0;
+  void* prev_out;       int64_t prev_stride;    int32_t prev_dtype;   int32_t S_overlap;
+                                                /* S_overlap != 0: S is written by the du_batch_sum launch that
+                                                 * IMMEDIATELY precedes this call on the stream; the step is then
+                                                 * launched as its programmatic dependent (its sampling pilot, which
+                                                 * does not read S, overlaps the sum's tail; griddepcontrol.wait
+                                                 * orders the first S read).  0: plain stream order.              */
   void* x0_out;         int64_t x0_stride;      /* nullable, prev_dtype                              */
   void* eps_out;        int64_t eps_out_stride; /* nullable, fp32                                    */
   float* mask_out;      int64_t mask_out_stride;/* nullable                                          */
@@ -289,6 +294,17 @@ int du_fused_supported(int64_t n, int score_dtype);
  * kernel (fused_step_kernel), 2 = the predictive single-pass kernel (fused_pred_kernel; slices of >= 4 trips with the
  * epsilon-prediction fp32 update).  Both give bit-identical results; benchmarks use this to name what they timed. */
 int du_fused_last_kernel(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * DPM-Solver++ multistep update of the `dpm_2_uncertainty_centered` scheduler
+ * (SU/scheduling_dpm_2_uncertainty_centered.py:617-620 first order, :686-700 second order midpoint / heun):
+ *   out = (a*sample + b*m0) + c*(k*(m0 - m1))        one rounding per operation; m1 == NULL: out = a*sample + b*m0
+ * with the host scalars a = sigma_t/sigma_s0, b = -(alpha_t (exp(-h) - 1)), k = 1/r0 and c = -0.5*(alpha_t (exp(-h) - 1))
+ * (midpoint) or alpha_t ((exp(-h) - 1)/h + 1) (heun).  m0 / m1 are the converted model outputs (x0 predictions).
+ * ---------------------------------------------------------------------------------------------- */
+int du_dpm_solver_update(const void* sample, int64_t s_stride, int s_dtype, const void* m0, int64_t m0_stride, int m0_dtype,
+                         const void* m1, int64_t m1_stride, int m1_dtype, float a, float b, float c, float k,
+                         int64_t B, int64_t n, void* out, int64_t out_stride, int out_dtype, du_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * N4 — flip-based uncertainty.  Tensors are [B, C, H, W] rows views (row = C*H*W elements).

@@ -252,8 +252,27 @@ def main():
     save("sd_percentile_guidance", lat=lat, emb=emb, t=501, a_hat=a_hat, **out)
 
 
+def main_dpm():
+    """`dpm_2_uncertainty_centered` (SU/scheduling_dpm_2_uncertainty_centered.py): the factory builds it from the DDPM
+    scheduler's config (get_uncertainty_scheduler.py:31-32).  `python tests/golden/make_golden.py dpm` writes only these."""
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    cls = "KDPM2SchedulerUncertaintyImagenetClassConditioned"
+    run_scheduler_case("sched_dpm2", "scheduling_dpm_2_uncertainty_centered", cls,
+                       dict(M=4, after_step=10, num_steps_uc=5), n_steps=20, seed=20,
+                       cfg_over=dict(variance_type="fixed_small"))
+    run_scheduler_case("sched_dpm2_heun_short", "scheduling_dpm_2_uncertainty_centered", cls,
+                       dict(M=3, after_step=4, num_steps_uc=4, solver_type="heun", final_sigmas_type="sigma_min"), n_steps=12, seed=21,
+                       cfg_over=dict(variance_type="learned_range", timestep_spacing="linspace", beta_schedule="squaredcos_cap_v2"))
+    run_scheduler_case("sched_dpm2_order1", "scheduling_dpm_2_uncertainty_centered", cls,
+                       dict(M=2, after_step=2, num_steps_uc=3, solver_order=1), n_steps=8, seed=22,
+                       cfg_over=dict(variance_type="fixed_small", timestep_spacing="trailing", beta_schedule="scaled_linear"))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "widen":
+    if len(sys.argv) > 1 and sys.argv[1] == "dpm":
+        main_dpm()
+    elif len(sys.argv) > 1 and sys.argv[1] == "widen":
         main_widen()
     else:
         main()

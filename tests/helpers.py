@@ -16,7 +16,7 @@ def l4_sampling_loop(scheduler, model, x_T, y, eta=0.0, slice_channels=None):
             t_tensor = torch.full((x.shape[0],), t, device=x.device, dtype=torch.long)
             x = scheduler.scale_model_input(x, t)
             eps = model(x, t_tensor, y=y)[:, :C]
-            out = scheduler.step(eps, t, x, eta=eta)
+            out = scheduler.step(eps, t, x, eta=eta) if eta != 0.0 else scheduler.step(eps, t, x)   # (the DPM-2 step has no eta)
             if scheduler.timestep_after_step >= t >= scheduler.timestep_end_step:
                 uncs.append(out.uncertainty.detach().cpu())
                 pe = out.pred_epsilon

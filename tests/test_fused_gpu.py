@@ -211,6 +211,45 @@ def test_fused_predictive_kernel_equals_three_phase_kernel_bitwise(ops, monkeypa
         assert bits_equal(out[1][kk], out[0][kk]), kk
 
 
+def test_fused_step_as_dependent_launch_of_the_batch_sum(ops):
+    """du_batch_sum -> fused step launched as its programmatic dependent (S_overlap): the step's pilot overlaps the sum, its S
+    reads are ordered by griddepcontrol.wait.  Same bits as the two launches in plain stream order; repeated to give a race
+    a chance to show; also replayed from a CUDA graph (the bench's timed region)."""
+    d = dev()
+    eps, scores, sample = synth(16, 3, 128, 5, seed=31)
+    c, k = coeffs_for(ops, 180, 160)
+    a_hat = float(torch.cumprod(1 - O.make_betas(), 0)[180])
+    sg, eg, xg = [s.to(d) for s in scores], eps.to(d), sample.to(d)
+    S_ref = ops.batch_sum(eg)
+    plain = ops.FusedStep(sg, eg, xg, 0.9, k, a_hat, S=S_ref, S_broadcast=True)
+    want = {kk: v.clone() for kk, v in plain.launch().items() if v is not None}
+    assert ops.fused_last_kernel() == "fused_pred_kernel"
+    S_buf = torch.empty_like(S_ref)
+    plan = ops.FusedStep(sg, eg, xg, 0.9, k, a_hat, S=S_buf, S_broadcast=True)
+    for rep in range(20):
+        S_buf.fill_(float("nan"))          # a step that read S before the sum finished would produce NaNs
+        r = plan.launch_with_batch_sum(eg, S_buf)
+        torch.cuda.synchronize()
+        for kk in want:
+            assert bits_equal(r[kk], want[kk]), (rep, kk)
+    assert plan.P.S_overlap == 0
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        plan.launch_with_batch_sum(eg, S_buf)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(3):
+            S_buf.fill_(float("nan"))
+            plan.launch_with_batch_sum(eg, S_buf)
+    for _ in range(3):
+        plan.res["prev"].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert bits_equal(plan.res["prev"], want["prev"]) and bits_equal(S_buf, S_ref)
+
+
 @pytest.mark.parametrize("q,higher", [(0.0, True), (1.0, True), (0.5, False), (0.999, True), (0.37, False)])
 def test_fused_quantile_edges(ops, q, higher):
     run_case(ops, 3, 3, 32, 4, q, "var_with_center", batch_sum=True, higher=higher, seed=7)
