@@ -1,7 +1,8 @@
 """String -> scheduler factory.  Mirrors diffusion_uncertainty/schedulers_uncertainty/get_uncertainty_scheduler.py:13-40
 (same `--scheduler-type` keys, same argparse attribute names, unknown keys fall through to MC-dropout).  Keys whose
-scheduler is outside the hot-path scope (`flip_grad`: per-parameter gradients upsampled to a map, autograd only;
-`dpm_2_uncertainty_centered`) raise NotImplementedError naming the row instead of silently picking another scheduler."""
+scheduler is outside the hot-path scope (`flip_grad`: per-parameter gradients upsampled to a map, autograd only) raise
+NotImplementedError naming the row instead of silently picking another scheduler."""
+from .scheduling_dpm_2_uncertainty_centered import KDPM2SchedulerUncertaintyImagenetClassConditioned as _DPM2Centered
 from .scheduling_ddim_flip import DDIMSchedulerUncertaintyImagenetClassConditioned as _Flip
 from .scheduling_ddim_mc_dropout import DDIMSchedulerUncertaintyImagenetClassConditioned as _MCDropout
 from .scheduling_ddim_uncertainty import DDIMSchedulerUncertaintyImagenetClassConditioned as _Uncertainty
@@ -10,7 +11,7 @@ from .scheduling_ddim_uncertainty_centered_d import DDIMSchedulerUncertaintyImag
 from .scheduling_ddim_uncertainty_image import DDIMSchedulerUncertaintyImagenetClassConditioned as _Image
 from .scheduling_ddim_uncertainty_zigzag_centered import DDIMSchedulerUncertaintyImagenetClassConditioned as _ZigZagCentered
 
-_NOT_ON_PATH = {"flip_grad", "dpm_2_uncertainty_centered"}
+_NOT_ON_PATH = {"flip_grad"}
 
 
 def get_uncertainty_scheduler(args, y, unet, scheduler):
@@ -32,6 +33,9 @@ def get_uncertainty_scheduler(args, y, unet, scheduler):
         return _Uncertainty.from_config(cfg, M=args.M, predict_next=False, **common)
     if kind == "uncertainty_centered_d":
         return _CenteredD.from_config(cfg, M=args.M, uncertainty_distance=args.uncertainty_distance, **common)
+    if kind == "dpm_2_uncertainty_centered":
+        # (the reference passes y= and eta= too; the DPM-2 constructor accepts neither, from_config drops them — :31-32)
+        return _DPM2Centered.from_config(cfg, M=args.M, **common)
     if kind == "uncertainty_zigzag_centered":
         return _ZigZagCentered.from_config(cfg, M=args.M, num_zigzag=args.num_zigzag, **common)
     return _MCDropout.from_config(cfg, prompt_embeds=y, M=args.M, **{k: v for k, v in common.items() if k != "y"})

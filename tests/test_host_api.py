@@ -233,10 +233,25 @@ def test_factory_keys():
     args.scheduler_type = "flip"
     fl = get_uncertainty_scheduler(args, "y", "unet", base)
     assert "Flip" in [c.__name__ for c in type(fl).__mro__] and fl.config.after_step == 3 and fl.prompt_embeds == "y"
-    for key in ("flip_grad", "dpm_2_uncertainty_centered"):
-        args.scheduler_type = key
+    args.scheduler_type = "flip_grad"
+    with pytest.raises(NotImplementedError):
+        get_uncertainty_scheduler(args, "y", "unet", base)
+    args.scheduler_type = "dpm_2_uncertainty_centered"
+    dp = get_uncertainty_scheduler(args, "y", "unet", base)
+    assert dp.__class__.__name__ == "KDPM2SchedulerUncertaintyImagenetClassConditioned" and dp.M == 4 and dp.unet == "unet"
+    assert dp.config.after_step == 3 and dp.config.beta_schedule == "linear" and dp.config.timestep_spacing == "leading"
+    assert dp.prompt_embeds is None and dp.class_conditioned is True      # y= is dropped, as in the reference (the loop assigns it)
+    dp.set_timesteps(10)
+    assert dp.timesteps.tolist() == [900, 810, 720, 630, 540, 450, 360, 270, 180, 90] and len(dp.sigmas) == 11
+    assert dp.timestep_after_step == 630 and dp.timestep_end_step == 540 and float(dp.sigmas[-1]) == 0.0
+    from diffusion_uncertainty_b200.schedulers_uncertainty.mixin import SchedulerUncertaintyClassConditionedMixin, SchedulerUncertaintyMixin
+    assert isinstance(dp, SchedulerUncertaintyMixin) and isinstance(dp, SchedulerUncertaintyClassConditionedMixin)
+    import diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_dpm_2_uncertainty_centered as dpm
+    for bad in ("dpmsolver", "sde-dpmsolver++"):
         with pytest.raises(NotImplementedError):
-            get_uncertainty_scheduler(args, "y", "unet", base)
+            dpm.KDPM2DiscreteSchedulerUncertainty(algorithm_type=bad)
+    with pytest.raises(ValueError, match="set_timesteps"):
+        dpm.KDPM2DiscreteSchedulerUncertainty().step(None, 0, None)
     assert instatiate_uc_scheduler is get_uncertainty_scheduler and instatiate_uncertainty_scheduler is get_uncertainty_scheduler
 
 

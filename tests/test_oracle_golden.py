@@ -72,6 +72,35 @@ def test_oracle_scheduler_matches_reference(golden_dir, case):
     assert same(res["final"].numpy(), g["final"])
 
 
+DPM_CASES = [
+    # name, ctor kwargs, n_steps, seed, config overrides (tests/golden/make_golden.py dpm)
+    ("sched_dpm2", dict(M=4, after_step=10, num_steps_uc=5), 20, 20, dict(variance_type="fixed_small", timestep_spacing="leading")),
+    ("sched_dpm2_heun_short", dict(M=3, after_step=4, num_steps_uc=4, solver_type="heun", final_sigmas_type="sigma_min"), 12, 21,
+     dict(variance_type="learned_range", timestep_spacing="linspace", beta_schedule="squaredcos_cap_v2")),
+    ("sched_dpm2_order1", dict(M=2, after_step=2, num_steps_uc=3, solver_order=1), 8, 22,
+     dict(variance_type="fixed_small", timestep_spacing="trailing", beta_schedule="scaled_linear")),
+]
+
+
+@pytest.mark.parametrize("case", DPM_CASES, ids=[c[0] for c in DPM_CASES])
+def test_oracle_dpm2_scheduler_matches_reference(golden_dir, case):
+    from oracle.du_oracle_dpm import OracleDPM2Scheduler
+    name, kw, n_steps, seed, cfg = case
+    g = load(golden_dir, name)
+    model = ToyADM(3, seed=seed).eval()
+    x_T, y = T(g["x_T"]), T(g["y"])
+    sched = OracleDPM2Scheduler(None, **kw, **cfg)
+    sched.predict = lambda x, t: model(x, t, y=sched.prompt_embeds)[:, :3]
+    sched.set_timesteps(n_steps)
+    assert sched.timestep_after_step == int(g["after"]) and sched.timestep_end_step == int(g["end"])
+    assert same(sched.timesteps.numpy(), g["timesteps"])
+    with seeded_noise(1000 + seed):
+        res = l4_sampling_loop(sched, model, x_T, y)
+    assert same(res["uncertainty"].numpy(), g["uncertainty"])
+    assert same(res["score"].numpy(), g["score"])
+    assert same(res["final"].numpy(), g["final"])
+
+
 def test_quantile_restatement_is_torch_quantile(golden_dir):
     g = load(golden_dir, "threshold_map")
     for tag in "abcdef":

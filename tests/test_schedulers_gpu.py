@@ -16,7 +16,7 @@ import pytest
 import torch
 
 from tests.helpers import l4_sampling_loop
-from tests.test_oracle_golden import SCHED_CASES, T, load, same
+from tests.test_oracle_golden import DPM_CASES, SCHED_CASES, T, load, same
 from tests.toy_models import ToyADM, ToySDUNet, seeded_noise
 
 pytestmark = pytest.mark.gpu
@@ -93,6 +93,44 @@ def test_scheduler_replays_the_reference_trajectory(golden_dir, case):
         diff = (res["final"] - T(g["final"])).abs()
         assert float((diff > 1e-5).float().mean()) < 0.01, "only threshold-straddling pixels may differ"
         assert same(res["prevs"][0].numpy(), g["prev_first"])      # before the window: plain DDIM, bit-exact
+
+
+@pytest.mark.parametrize("case", DPM_CASES, ids=[c[0] for c in DPM_CASES])
+def test_dpm2_scheduler_replays_the_reference_trajectory(golden_dir, case):
+    """dpm_2_uncertainty_centered: x0 conversion, first / second order solver updates (midpoint, heun), the re-noising and
+    the model inputs are bit-exact (one rounding per reference operation); the map within the fp32 bar"""
+    import diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_dpm_2_uncertainty_centered as dpm
+    name, kw, n_steps, seed, cfg = case
+    g = load(golden_dir, name)
+    model = ToyADM(3, seed=seed).eval().to(dev())
+    sched = dpm.KDPM2SchedulerUncertaintyImagenetClassConditioned.from_config(
+        {**dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True,
+                set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", timestep_spacing="leading"), **cfg},
+        unet=model, **kw)
+    sched.set_timesteps(n_steps)
+    assert sched.timestep_after_step == int(g["after"]) and sched.timestep_end_step == int(g["end"])
+    assert same(sched.timesteps.numpy(), g["timesteps"])
+    x_T, y = T(g["x_T"]).to(dev()), T(g["y"]).to(dev())
+    with seeded_noise(1000 + seed):
+        res = l4_sampling_loop(sched, model, x_T, y)
+    assert same(res["final"].numpy(), g["final"]), "x_{t-1} trajectory must be bit-exact"
+    assert same(res["score"].numpy(), g["score"])
+    assert same(res["prevs"][0].numpy(), g["prev_first"]) and same(res["prevs"][len(res["prevs"]) // 2].numpy(), g["prev_mid"])
+    assert rel_close(res["uncertainty"], g["uncertainty"], 1e-5, atol=1e-12)
+    # same trajectory with torch's CUDA generator: in-kernel draws == torch.randn_like + du_perturb
+    outs = []
+    for fuse in (True, False):
+        from diffusion_uncertainty_b200 import ops as o
+        orig = o.randn_fusable
+        if not fuse:
+            o.randn_fusable = lambda *a, **k: False
+        try:
+            torch.manual_seed(5)
+            sched.set_timesteps(n_steps)
+            outs.append(l4_sampling_loop(sched, model, x_T, y))
+        finally:
+            o.randn_fusable = orig
+    assert same(outs[0]["final"].numpy(), outs[1]["final"].numpy()) and same(outs[0]["uncertainty"].numpy(), outs[1]["uncertainty"].numpy())
 
 
 def test_step_outputs_and_window(golden_dir):
