@@ -340,7 +340,7 @@ def run_ours(args):
     from diffusion_uncertainty_b200.host_step import HostStreamedUncertaintyStep
     h_prev = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
     h_map = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     host_step = HostStreamedUncertaintyStep(B, (C, H, W), M, dev, score_dtype=dtype, chunks=args.e2e_chunks)
 
     def e2e_step(i):
@@ -527,7 +527,7 @@ def main():
     ap.add_argument("--batch-sum", type=int, default=1, help="1 = reference behaviour (posterior sum over the batch axis)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--unfused", action="store_true", help="time the 3-kernel chain instead of the single fused launch")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="image chunks of the host-buffer pipeline (e2e leg)")
+    ap.add_argument("--e2e-chunks", type=int, default=1, help="image chunks of the host-buffer pipeline (e2e leg)")
     ap.add_argument("--eager", action="store_true", help="time K eager launches from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -390,12 +390,17 @@ static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t sm
 
 template <typename T, int MT, bool OUTS>
 static int launch_pred_m(const PredKParams& pk, const FusedPlan& plan, int threads, size_t smem, cudaStream_t st) {
+#ifdef DU_PRED_DEV   // development builds: one thread configuration (csrc/build.sh -DDU_PRED_DEV), a third of the compile time
+  if (threads != 512) return 0;
+  return launch_pred_t<T, MT, 512, 2, OUTS>(pk, plan, smem, st);
+#else
   switch (threads) {
     case 1024: return launch_pred_t<T, MT, 1024, 1, OUTS>(pk, plan, smem, st);
     case 768: return launch_pred_t<T, MT, 768, 1, OUTS>(pk, plan, smem, st);
     case 384: return launch_pred_t<T, MT, 384, 2, OUTS>(pk, plan, smem, st);
     default: return launch_pred_t<T, MT, 512, 2, OUTS>(pk, plan, smem, st);
   }
+#endif
 }
 
 template <typename T>

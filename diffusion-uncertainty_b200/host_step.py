@@ -9,7 +9,10 @@ pipelined over three streams:
     compute stream    du_fused_uncertainty_step on chunk k           (per-image work: chunks are independent)
     copy-out stream   D2H of chunk k-1 (x_{t-1}, map)
 
-so the step costs about max(H2D, D2H) instead of H2D + kernel + D2H.  The one thing that couples images — the
+so the step costs about max(H2D, D2H) instead of H2D + kernel + D2H.  Consecutive calls pipeline too: the next call's H2D
+starts as soon as this call's last kernel has consumed the staging buffers (it does not wait for this call's D2H — PCIe is
+full duplex), and its first kernel waits for this call's last D2H before it overwrites the output staging buffers.  The
+one thing that couples images — the
 reference's posterior sum over the batch axis (`pred_epsilon.sum(dim=0)`, uncertainty_guidance.py:119) — is handled
 by sending eps for the whole batch first and reducing it (du_batch_sum) before the first chunk is updated.
 Device staging buffers are allocated once and reused by every call.
@@ -41,6 +44,8 @@ class HostStreamedUncertaintyStep:
         self.d_S = torch.empty(self.shape, device=d, dtype=torch.float32)
         self.s_in, self.s_out = torch.cuda.Stream(device=d), torch.cuda.Stream(device=d)
         self.bounds = [(k * self.B // self.chunks, (k + 1) * self.B // self.chunks) for k in range(self.chunks)]
+        self._inputs_free: Optional[torch.cuda.Event] = None    # previous call's last kernel is done with d_scores / d_eps / d_sample
+        self._outputs_free: Optional[torch.cuda.Event] = None   # previous call's last D2H is done with d_prev / d_map
 
     def __call__(self, h_scores: List[torch.Tensor], h_eps: torch.Tensor, h_sample: torch.Tensor, q: float, coeffs,
                  alpha_hat_t: float, out_prev: torch.Tensor, out_map: torch.Tensor, batch_sum: bool = True,
@@ -51,8 +56,11 @@ class HostStreamedUncertaintyStep:
         if len(h_scores) != self.M:
             raise ValueError(f"expected {self.M} score tensors, got {len(h_scores)}")
         main = torch.cuda.current_stream(self.device)
-        self.s_in.wait_stream(main)
-        self.s_out.wait_stream(main)
+        if self._inputs_free is None:
+            self.s_in.wait_stream(main)
+            self.s_out.wait_stream(main)
+        else:
+            self.s_in.wait_event(self._inputs_free)
         u_dst = map_slot if map_slot is not None else self.d_map
         with torch.cuda.stream(self.s_in):
             self.d_eps.copy_(h_eps, non_blocking=True)           # whole batch first: the batch-axis sum needs all of it
@@ -76,6 +84,8 @@ class HostStreamedUncertaintyStep:
             main.wait_event(in_ready[k])
             if k == 0:
                 main.wait_event(eps_ready)
+                if self._outputs_free is not None:
+                    main.wait_event(self._outputs_free)
             ops.uncertainty_step([s[a:b] for s in self.d_scores], self.d_eps[a:b], self.d_sample[a:b], q, coeffs, alpha_hat_t,
                                  precomputed_sum=S, batch_sum=batch_sum, map_out=u_dst[a:b], prev_out=self.d_prev[a:b])
             done = torch.cuda.Event()
@@ -86,5 +96,12 @@ class HostStreamedUncertaintyStep:
                 out_map[a:b].copy_(u_dst[a:b], non_blocking=True)
                 last = torch.cuda.Event()
                 last.record(self.s_out)
-        main.wait_stream(self.s_out)
+        self._inputs_free = torch.cuda.Event()
+        self._inputs_free.record(main)
+        self._outputs_free = last
         return last
+
+    def synchronize(self):
+        """Wait for every transfer of every call so far (the staging buffers and the host outputs are then quiescent)."""
+        if self._outputs_free is not None:
+            self._outputs_free.synchronize()

@@ -695,7 +695,7 @@ class FusedStep:
                  S: Optional[torch.Tensor] = None, S_broadcast: bool = False, higher: bool = True,
                  map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
                  want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None,
-                 prev_out: Optional[torch.Tensor] = None):
+                 prev_out: Optional[torch.Tensor] = None, S_overlap: bool = False):
         M = len(scores)
         if M < 1 or M > L.DU_MAX_M:
             raise ValueError(f"fused step: M={M} must be in [1, {L.DU_MAX_M}]")
@@ -723,6 +723,9 @@ class FusedStep:
             if sr.n != r0.n:
                 raise ValueError("fused step: S has the wrong number of elements per image")
             P.S, P.S_stride, P.S_broadcast = sr.ptr, sr.stride, int(S_broadcast)
+            # S_overlap: the caller guarantees that the du_batch_sum writing S is the launch right before this one on the
+            # stream; the step then starts as its programmatic dependent (see launch_with_batch_sum)
+            P.S_overlap = int(bool(S_overlap))
         P.higher, P.q, P.lerp_fma = int(higher), float(q), int(bool(lerp_fma))
         P.post_M = float(M if post_M is None else post_M)
         P.inv_alpha_hat = float(1.0 / alpha_hat_t)
@@ -823,17 +826,18 @@ def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: 
     for t in list(scores) + [eps, sample]:
         _require_cuda(t, "uncertainty_step input")
     src = eps if sum_source is None else sum_source
-    S, bcast = (None if sum_source is None else src), False
+    S, bcast, summed_here = (None if sum_source is None else src), False, False
     if batch_sum and precomputed_sum is not None:
         S, bcast = precomputed_sum, True
     elif batch_sum and eps.shape[0] > 1:
-        S, bcast = batch_sum_fn(src), True
+        S, bcast, summed_here = batch_sum_fn(src), True, True
     if fused is None:
         fused = _fused_eligible(scores, eps, sample, map_out, S)
     if fused:
+        # (the fused launch directly follows the du_batch_sum above on this stream: it may start as its dependent launch)
         return fused_uncertainty_step(scores, eps, sample, q, coeffs, alpha_hat_t, moments_mode=moments_mode, S=S,
                                       S_broadcast=bcast, higher=higher, map_out=map_out, lerp_fma=lerp_fma, want_x0=want_x0,
-                                      want_eps=want_eps, want_mask=want_mask, prev_out=prev_out)
+                                      want_eps=want_eps, want_mask=want_mask, prev_out=prev_out, S_overlap=summed_here)
     u = moments(scores, center=eps, mode=moments_mode, out=map_out)
     thr = quantile_threshold(u, q, lerp_fma=lerp_fma)
     r = guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=src if S is None else S, aux_broadcast=bcast,

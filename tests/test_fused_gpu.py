@@ -370,3 +370,30 @@ def test_host_streamed_step_matches_the_device_step(ops, batch_sum):
            batch_sum=batch_sum, map_slot=buf[:, 1]).synchronize()
     assert bits_equal(h_map, want["u"]) and bits_equal(buf[:, 1], want["u"]) and bits_equal(h_prev, want["prev"])
     assert float(buf[:, 0].abs().max()) == 0.0
+
+
+def test_host_streamed_steps_pipeline_across_calls(ops):
+    """back-to-back calls without a host synchronisation in between: the next call's H2D overlaps this call's D2H and reuses
+    the staging buffers; every call must still deliver ITS result (different inputs per call, larger images so that the
+    transfers really overlap)"""
+    from diffusion_uncertainty_b200.host_step import HostStreamedUncertaintyStep
+    d = dev()
+    B, C, H, M, calls = 24, 3, 128, 5, 4
+    c, k = coeffs_for(ops, 180, 160)
+    a_hat = float(torch.cumprod(1 - O.make_betas(), 0)[180])
+    ins, wants, outs = [], [], []
+    for j in range(calls):
+        eps, scores, sample = synth(B, C, H, M, seed=40 + j)
+        ins.append(([s.pin_memory() for s in scores], eps.pin_memory(), sample.pin_memory()))
+        wants.append({kk: v.clone() for kk, v in ops.uncertainty_step([s.to(d) for s in scores], eps.to(d), sample.to(d), 0.9, k, a_hat,
+                                                                       batch_sum=True).items() if v is not None})
+        outs.append((torch.empty(B, C, H, H).pin_memory(), torch.empty(B, C, H, H).pin_memory()))
+    hs = HostStreamedUncertaintyStep(B, (C, H, H), M, d, chunks=3)
+    for rep in range(3):
+        for o in outs:
+            o[0].zero_(); o[1].zero_()
+        for j in range(calls):
+            hs(ins[j][0], ins[j][1], ins[j][2], 0.9, k, a_hat, outs[j][0], outs[j][1], batch_sum=True)
+        hs.synchronize()
+        for j in range(calls):
+            assert bits_equal(outs[j][0], wants[j]["prev"]) and bits_equal(outs[j][1], wants[j]["u"]), (rep, j)
