@@ -28,8 +28,8 @@ PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu --eager > gpurun_out/ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused_ -s 4 -c 1 -o gpurun_out/fused_full -f python bench.py --steps 3 --warmup 3 --no-cpu --eager > gpurun_out/ncu_full.log 2>&1
 # summarise the capture ON THE BOX (the report itself is larger than what gpurun copies back)
-python tools/ncu_summary.py gpurun_out/fused_full.ncu-rep ${TAG:-r1_v4_fused} gpurun_out > gpurun_out/ncu_summary.log 2>&1
-ncu -i gpurun_out/fused_full.ncu-rep --page details --csv > gpurun_out/${TAG:-r1_v4_fused}_ncu_details.csv 2>/dev/null
+python tools/ncu_summary.py gpurun_out/fused_full.ncu-rep ${TAG:-r1_v5_fused} gpurun_out > gpurun_out/ncu_summary.log 2>&1
+ncu -i gpurun_out/fused_full.ncu-rep --page details --csv > gpurun_out/${TAG:-r1_v5_fused}_ncu_details.csv 2>/dev/null
 rm -f gpurun_out/fused_full.ncu-rep
 cat gpurun_out/smoke.log | tail -5
 ls -la gpurun_out | head -40
