@@ -20,7 +20,7 @@ constexpr int H0_BINS = 1 << H0_BITS, H1_BINS = 1 << H1_BITS, H2_BINS = 1 << H2_
 constexpr int H0_WORDS = H0_BINS / 2;
 // work area behind the level-0 histogram: [0, LIST_CAP) candidate keys of the selected level-0 bin, [LIST_CAP, +H1_BINS) their
 // level-1 histogram.  The general path (heavy ties) reuses the area as level-1 / level-2 histograms of the whole slice.
-constexpr int LIST_CAP = 1024;
+constexpr int LIST_CAP = 1024;   // (the predictive kernel keeps a larger list: PRED_LIST_CAP in du_fused_pred.cu)
 constexpr int WORK_WORDS = LIST_CAP + H1_BINS;
 constexpr int HIST_WORDS = H0_WORDS + WORK_WORDS;
 // misc words: [0..2] locate result, [3] nan flag, [4] min larger key, [5] next bin, [6] candidate count, [7] threshold,

@@ -23,6 +23,15 @@ namespace du {
 // If the verification fails (band missed, NaN, ties overflowing the lists) the image falls back to the exact select over
 // the map in L2 and a full update pass: always the exact result, only slower.
 // =====================================================================================================================
+// Capacity of the key list of the selected level-0 bin.  That bin holds n * (probability mass of one bin) keys — about 920 of
+// the 49152 of an ImageNet-128 image at q = 0.9 (measured: 915..1025 over 1024 images).  With LIST_CAP = 1024 one image in a
+// thousand took the general path and held the whole launch back by 20 us (seen as one slow rank at N = 4); 2048 entries leave
+// more than 30 standard deviations.  The three-phase kernel keeps 1024 (its shared memory is sized by the map).
+constexpr int PRED_LIST_CAP = 2048;
+constexpr int PRED_WORK_WORDS = PRED_LIST_CAP + H1_BINS;
+static_assert(PRED_LIST_CAP <= H0_WORDS, "list_select parks the tiny list in the level-0 histogram's words");
+static_assert(PRED_WORK_WORDS >= WORK_WORDS && PRED_WORK_WORDS >= H0_WORDS, "the general path and the pilot histogram reuse the work area");
+
 struct PredKParams {
   FusedKParams k;
   uint32_t trips;       // row trips per thread: ceil(groups per slice / THREADS)
@@ -68,7 +77,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* h0 = reinterpret_cast<uint32_t*>(smem_raw);   // full level-0 histogram (packed 16-bit)
   uint32_t* work = h0 + H0_WORDS;                         // key list + level-1 histogram (or the fallback's levels 1 / 2)
-  uint32_t* misc = work + WORK_WORDS;
+  uint32_t* misc = work + PRED_WORK_WORDS;
   // The pilot histogram (packed 16-bit) shares the work area: peers read it through DSMEM only during their band search,
   // which every CTA acknowledges with a cluster-barrier arrival; the matching wait sits after the streaming pass, and only
   // then is the area cleared for the select.
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   float* cand_e = reinterpret_cast<float*>(cand_idx + pk.cand_max);
   float* cand_s = cand_e + pk.cand_max;
 
-  for (int j = tid; j < HIST_WORDS; j += THREADS) h0[j] = 0;
+  for (int j = tid; j < H0_WORDS + PRED_WORK_WORDS; j += THREADS) h0[j] = 0;
   if (tid < MISC_WORDS) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
   __syncthreads();
   stamp(kp, 0);
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   if (__any_sync(0xffffffffu, nan_seen) && lane == 0) misc[3] = 1u;
   stamp(kp, 2);
   if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // nobody reads this CTA's pilot histogram any more
-  for (int j = tid; j < WORK_WORDS; j += THREADS) work[j] = 0;
+  for (int j = tid; j < PRED_WORK_WORDS; j += THREADS) work[j] = 0;
 
   // ---------------------------------------------------------------- finish: verify the band, exact select, patch
   sync_all();   // full histograms, candidate lists and flags of every CTA are complete
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
     d0 = misc[0]; below0 = misc[1];
     const uint32_t cnt0 = misc[2];
     __syncthreads();
-    bad = !(d0 >= lb_bin && d0 < ub_bin) || cnt0 > (uint32_t)LIST_CAP;
+    bad = !(d0 >= lb_bin && d0 < ub_bin) || cnt0 > (uint32_t)PRED_LIST_CAP;
   }
   stamp(kp, 3);
   float thr;
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
     redo = true;
   } else {
     uint32_t* list = work;
-    uint32_t* h1 = work + LIST_CAP;
+    uint32_t* h1 = work + PRED_LIST_CAP;
     const uint32_t want = d0 << LOW;
     const uint32_t ncand = misc[44];
     for (uint32_t i = tid; i < ncand; i += THREADS) {
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
 }
 
 
-static constexpr size_t kPredFixedBytes = (size_t)(H0_WORDS + WORK_WORDS + MISC_WORDS) * 4;
+static constexpr size_t kPredFixedBytes = (size_t)(H0_WORDS + PRED_WORK_WORDS + MISC_WORDS) * 4;
 
 template <typename T, int MT, int THREADS, int MINB, bool OUTS>
 static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t smem, cudaStream_t st) {

@@ -211,6 +211,37 @@ def test_fused_predictive_kernel_equals_three_phase_kernel_bitwise(ops, monkeypa
         assert bits_equal(out[1][kk], out[0][kk]), kk
 
 
+@pytest.mark.parametrize("M,lo_occ,hi_occ", [(5, 1100, 2048), (8, 1800, 2300)])
+def test_fused_dense_level0_bin_keeps_exact_results(ops, monkeypatch, M, lo_occ, hi_occ):
+    """Perturbations with a common component concentrate the map's distribution: the level-0 bin that holds the 90 % rank of
+    a 3x128x128 image then has ~1400 keys at M = 5 (ImageNet-128 with iid perturbations: ~920, up to 1025 in 1024 images —
+    which used to overflow a 1024-entry list and push the whole launch onto the general path), and ~2000 at M = 8, on both
+    sides of the 2048-entry list.  Exact threshold (torch.quantile of the kernel's map) and both kernels bit-identical."""
+    d = dev()
+    g = torch.Generator().manual_seed(77)
+    eps = torch.randn(4, 3, 128, 128, generator=g)
+    scores = [eps + 0.05 * (((-1.0) ** m) + 0.5 * torch.randn(4, 3, 128, 128, generator=g)) for m in range(M)]
+    sample = torch.randn(4, 3, 128, 128, generator=g)
+    c, k = coeffs_for(ops, 180, 160)
+    a_hat = float(torch.cumprod(1 - O.make_betas(), 0)[180])
+    sg, eg, xg = [s.to(d) for s in scores], eps.to(d), sample.to(d)
+    out = {}
+    for pred in (1, 0):
+        monkeypatch.setenv("DU_FUSED_PRED", str(pred))
+        r = ops.fused_uncertainty_step(sg, eg, xg, 0.9, k, a_hat, want_mask=True)
+        torch.cuda.synchronize()
+        out[pred] = {kk: v.clone() for kk, v in r.items() if v is not None}
+    u = out[1]["u"].cpu()
+    keys = u.flatten(1).view(torch.int32)
+    lo = int(0.9 * (keys.shape[1] - 1))
+    d0 = keys.sort(dim=1).values[:, lo] >> 19
+    occupancy = ((keys >> 19) == d0[:, None]).sum(1)
+    assert lo_occ < int(occupancy.min()) and int(occupancy.max()) < hi_occ, occupancy       # the case this test is about
+    assert bits_equal(out[1]["thr"], torch.quantile(u.flatten(1), 0.9, dim=1))
+    for kk in out[1]:
+        assert bits_equal(out[1][kk], out[0][kk]), kk
+
+
 def test_fused_step_as_dependent_launch_of_the_batch_sum(ops):
     """du_batch_sum -> fused step launched as its programmatic dependent (S_overlap): the step's pilot overlaps the sum, its S
     reads are ordered by griddepcontrol.wait.  Same bits as the two launches in plain stream order; repeated to give a race
