@@ -412,6 +412,112 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------- M-sharded arm
+def run_msharded(args):
+    """BASELINE config 5 (Stable Diffusion 512 px: one 4x64x64 latent, M = 16 perturbed predictions SHARDED over the ranks):
+    every rank reduces its M/R predictions to per-element partial moments (du_moments, DU_MOM_PARTIAL_M2), ONE all-gather of
+    the packed (mean, M2) pairs over NCCL, du_moments_merge (Chan, rank order), then the latent-sized rest of the step
+    (quantile, posterior blend, DDIM) replicated on every rank.  Strong scaling of one step; latency-bound by design
+    (1.3 MB of scores in total) — the line reports microseconds per step next to the Mpix/s."""
+    import torch.distributed as dist
+    from diffusion_uncertainty_b200 import distributed as D
+    from diffusion_uncertainty_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, C, H, W, M, q = WORKLOADS[args.workload]
+    sc = ddim_scalars()
+    coeffs = ops.make_coeffs(sc["sqrt_alpha_t"], sc["sqrt_beta_t"], sc["sqrt_alpha_prev"], sc["dir_coef"], clip_sample=False)
+    eps_h, scores_h, sample_h = synth_host(B, C, H, W, M, torch.float32, 1234, pin=False)     # same data on every rank
+    a, b = D.shard_range(M, rank, world)
+    eps, sample, mine = eps_h.to(dev), sample_h.to(dev), [s.to(dev) for s in scores_h[a:b]]
+    sm = D.ShardedMoments()
+
+    def step(i):
+        u = sm.reduce(mine, eps, "var_with_center", total_M=M)
+        thr = ops.quantile_threshold(u, q)
+        return ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=eps, post_M=float(M),
+                               inv_alpha_hat=1.0 / sc["alpha_hat"], want_eps=False)["prev"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 10)):
+        out = step(i)
+    barrier()
+    # K steps in ONE CUDA graph (the kernels and the NCCL all-gather are capturable: no host reads with total_M given), so the
+    # timed region holds GPU work only; --eager times K steps launched from Python instead
+    graph = None
+    if not args.eager:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                step(i)
+        torch.cuda.current_stream().wait_stream(side)
+        barrier()
+        launches0 = ops.launch_count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(args.steps):
+                out = step(i)
+        launches = ops.launch_count - launches0
+        barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        for i in range(3 if graph is not None else 200):
+            graph.replay() if graph is not None else step(i)
+        barrier()
+        launches0 = ops.launch_count
+        e0.record()
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(args.steps):
+                out = step(i)
+        e1.record()
+        if graph is None:
+            launches = ops.launch_count - launches0
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        # all ranks must hold the same x_{t-1}
+        ref = out.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([int(torch.equal(ref, out))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        identical = bool(same.item())
+    else:
+        identical = True
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        n_el = B * C * H * W
+        line = {"metric": "uncertainty_step_throughput", "value": B * H * W / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 10), "ms_per_step": ms_per_step,
+                "us_per_step": ms_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "shape": [B, C, H, W], "M": M, "q": q,
+                           "parallelism": f"M sharded x{world} ({b - a} predictions per rank), one NCCL all-gather of (mean, M2), "
+                                          "replicated quantile / posterior / DDIM",
+                           "chain": "du_moments(partial) -> all_gather -> du_moments_merge -> du_quantile_threshold -> du_guided_step",
+                           "l2": "1.3 MB of scores: latency-bound, L2-resident"},
+                "timed_region": "one CUDA graph of K steps (kernels + NCCL all-gather)" if graph is not None else "K eager steps",
+                "collective_bytes_per_step": 2 * n_el * 4 * world, "x_prev_identical_on_all_ranks": identical,
+                "gpu_launches": launches, "clocks": clocks.summary("200 untimed steps + the K timed steps")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------- sampling-loop arm
 LOOPS = {
     # name: (feeder factory, total batch, C, H, betas, scheduler kwargs, generation steps)
@@ -540,6 +646,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--unfused", action="store_true", help="time the 3-kernel chain instead of the single fused launch")
     ap.add_argument("--e2e-chunks", type=int, default=1, help="image chunks of the host-buffer pipeline (e2e leg)")
+    ap.add_argument("--shard-m", action="store_true", help="shard the M predictions over the ranks (SD-512 latent workload) instead of the batch")
     ap.add_argument("--seed-offset", type=int, default=0, help="added to the data seed 1234 + rank (to replay another rank's data on one GPU)")
     ap.add_argument("--eager", action="store_true", help="time K eager launches from Python instead of one CUDA graph of K steps")
     args = ap.parse_args()
@@ -553,6 +660,8 @@ def main():
         run_loop(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.shard_m:
+        run_msharded(args)
     else:
         run_ours(args)
 

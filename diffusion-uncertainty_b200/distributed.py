@@ -84,9 +84,13 @@ class ShardedMoments:
         from . import ops
         return ops.moments_merge(means, m2s, counts, mode=mode)
 
-    def reduce(self, local_scores: Sequence[torch.Tensor], center: Optional[torch.Tensor], mode: str) -> torch.Tensor:
+    def reduce(self, local_scores: Sequence[torch.Tensor], center: Optional[torch.Tensor], mode: str,
+               total_M: Optional[int] = None) -> torch.Tensor:
         """mode: 'var' (F1b), 'var_with_center' (F1c: the centre counts as one more sample, contributed by rank 0 only)
-        or 'centered' (F1a: sum of squared deviations about the common centre / total M)."""
+        or 'centered' (F1a: sum of squared deviations about the common centre / total M).
+        total_M: the number of samples over all ranks when they were dealt out with `shard_samples` — the per-rank counts
+        are then known arithmetically, the step is ONE collective (the packed partials) and never reads a device value
+        on the host; without it the counts are exchanged too (one more small all-gather and a host read)."""
         if mode not in ("var", "var_with_center", "centered"):
             raise ValueError(f"ShardedMoments: unsupported mode {mode!r}")
         n_local = len(local_scores)
@@ -104,10 +108,17 @@ class ShardedMoments:
         packed = torch.stack([mean.float(), m2.float()], dim=0).contiguous()          # [2, ...]
         gathered = torch.empty((self.world,) + tuple(packed.shape), device=packed.device, dtype=packed.dtype)
         dist.all_gather_into_tensor(gathered.view(self.world * packed.shape[0], *packed.shape[1:]), packed, group=self.group)
-        counts_t = torch.tensor([count], device=packed.device, dtype=torch.int64)
-        all_counts = torch.empty(self.world, device=packed.device, dtype=torch.int64)
-        dist.all_gather_into_tensor(all_counts, counts_t, group=self.group)
-        counts = [int(c) for c in all_counts.tolist()]
+        if total_M is not None:
+            counts = [shard_samples(total_M, r, self.world) + (1 if (mode == "var_with_center" and r == 0) else 0)
+                      for r in range(self.world)]
+            if counts[self.rank] != count:
+                raise ValueError(f"ShardedMoments: rank {self.rank} holds {n_local} samples, shard_samples({total_M}) says "
+                                 f"{shard_samples(total_M, self.rank, self.world)}")
+        else:
+            counts_t = torch.tensor([count], device=packed.device, dtype=torch.int64)
+            all_counts = torch.empty(self.world, device=packed.device, dtype=torch.int64)
+            dist.all_gather_into_tensor(all_counts, counts_t, group=self.group)
+            counts = [int(c) for c in all_counts.tolist()]
         means = [gathered[r, 0] for r in range(self.world)]
         m2s = [gathered[r, 1] for r in range(self.world)]
         return self._merge(means, m2s, counts, "centered" if mode == "centered" else "var")

@@ -80,6 +80,10 @@ def worker(rank, world, port, M, tmp):
                            ("centered", O.centered_second_moment(scores, eps))):
             got = sm.reduce(scores[a:b], eps, mode)
             assert torch.allclose(got, want, rtol=1e-5, atol=1e-9), (mode, (got - want).abs().max())
+            got_m = sm.reduce(scores[a:b], eps, mode, total_M=M)      # counts known arithmetically: one collective only
+            assert torch.equal(got_m, got), mode
+        with pytest.raises(ValueError, match="shard_samples"):
+            sm.reduce(scores[a:b], eps, "var", total_M=M + 2 * world + 1)
         # batch sharding: whole-batch z-norm statistics and the batch-axis sum
         u = torch.rand(6, 3, 8, 8, generator=g) ** 2
         (mine,) = D.shard_batch([u], rank, world)
