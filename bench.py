@@ -514,7 +514,14 @@ def run_msharded(args):
                 "collective_bytes_per_step": 2 * n_el * 4 * world, "x_prev_identical_on_all_ranks": identical,
                 "gpu_launches": launches, "clocks": clocks.summary("200 untimed steps + the K timed steps")}
         print(json.dumps(line), flush=True)
+    # the graph holds captured NCCL kernels: release it (and drain the device) BEFORE the communicator goes away, otherwise
+    # the teardown can wait forever
+    graph = None
+    del out
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
