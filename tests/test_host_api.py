@@ -67,6 +67,38 @@ def test_no_cpu_fallback():
         ops.ddim_step(x, x, ops.make_coeffs(1.0, 0.0, 1.0, 0.0))
 
 
+def test_in_kernel_noise_has_no_cpu_path():
+    """the draw is fused only for dense CUDA tensors; CPU tensors never reach a kernel and never get a silent torch fallback"""
+    from diffusion_uncertainty_b200 import ops
+    x = torch.randn(2, 3, 8, 8)
+    assert ops.randn_fusable(x) is False
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.perturb_randn(x, 0.9, 0.1)
+    with pytest.raises(RuntimeError):
+        ops.randn_like(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.perturb_fresh(x, 0.9, 0.1)           # torch.randn_like, then du_perturb refuses the CPU tensors
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.dpm_solver_update(x, x, None, 1.0, 1.0)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm: oracle port on the host cores) — one JSON line with the contract's keys"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3",
+                          "--workload", "cifar10_ddpm_b16_m5"], capture_output=True, text=True, check=True, timeout=300).stdout
+    d = json.loads(out.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "cifar10_ddpm_b16_m5" and d["steps"] == 1
+    loop = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "imagenet128_adm_loop"],
+                          capture_output=True, text=True, check=True, timeout=120).stdout
+    assert json.loads(loop.strip().splitlines()[-1])["impl"] == "reference"
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "diffusion-uncertainty_b200")
     for dirpath, _, files in os.walk(pkg):
@@ -81,7 +113,8 @@ SU = "diffusion_uncertainty_b200.schedulers_uncertainty."
 MODULES = ["scheduling_ddim_uncertainty_zigzag_centered", "scheduling_ddim_uncertainty_zigzag", "scheduling_ddim_uncertainty_centered",
            "scheduling_ddim_uncertainty_centered_d", "scheduling_ddim_uncertainty", "scheduling_ddim_uncertainty_image",
            "scheduling_ddim_infer_noise", "scheduling_ddim_mc_dropout", "scheduling_ddim_uncertainty_threshold",
-           "scheduling_ddim_infer_noise_multiscale_threshold"]
+           "scheduling_ddim_infer_noise_multiscale_threshold", "scheduling_ddim_flip", "scheduling_ddim_flip_threshold",
+           "scheduling_ddim_uncertainty_grad", "scheduling_ddim_mc_dropout_gradient"]
 CLASSES = ["DDIMSchedulerUncertainty", "DDIMSchedulerUncertaintyImagenet", "DDIMSchedulerUncertaintyCifar10",
            "DDIMSchedulerUncertaintyImagenetClassConditioned"]
 
