@@ -62,7 +62,8 @@ __device__ __forceinline__ void moments_group(const du_fused_params& p, int64_t 
   raw_c = make_uint4(0u, 0u, 0u, 0u);
   const uint32_t byte_off = g_elems * (uint32_t)sizeof(T);
   if (centre_mode) raw_c = ldg_stream_128_at(reinterpret_cast<const T*>(p.eps) + erow, byte_off);
-  if constexpr (MT > 0) accumulate_scores_ct<T, MT>(p.scores, srow, byte_off, raw_c, centre_mode, false, centre_mode != 1, c, k, s1, s2);
+  // the scores are read exactly once: L2 evict-first, so that they do not displace eps (kept by du_batch_sum) and the outputs
+  if constexpr (MT > 0) accumulate_scores_ct<T, MT, true>(p.scores, srow, byte_off, raw_c, centre_mode, false, centre_mode != 1, c, k, s1, s2, kL2EvictFirst);
   else accumulate_scores<T>(p.scores, p.M, srow + g_elems, raw_c, centre_mode, false, centre_mode != 1, c, k, s1, s2);
 #pragma unroll
   for (int e = 0; e < VEC; ++e) {
@@ -539,7 +540,7 @@ __device__ __forceinline__ void guided_update_slice(const FusedKParams& kp, cons
   for (int g = tid; g < ng4; g += THREADS, ++trip) {
     float s[4], e0[4], S[4];
     if (FAST) {
-      const uint4 r = ldg_stream_128(reinterpret_cast<const float*>(p.sample) + xrow + 4 * g);
+      const uint4 r = ldg_stream_128_pol(reinterpret_cast<const float*>(p.sample) + xrow + 4 * g, kL2EvictFirst);
       s[0] = __uint_as_float(r.x); s[1] = __uint_as_float(r.y); s[2] = __uint_as_float(r.z); s[3] = __uint_as_float(r.w);
     } else {
       load4(p.sample, xrow + 4 * g, p.sample_dtype, s);
