@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Build libdu_b200.so (sm_100a only) next to the Python package.  Usage: csrc/build.sh [extra nvcc flags]
-# Objects are rebuilt only when their .cu, any header of csrc/ or include/, or this script is newer (DU_REBUILD=1 forces all;
-# extra nvcc flags also force all).
+# Objects are rebuilt only when their .cu, any header of csrc/ or include/, or this script is newer, or when they were built
+# with other extra flags than this call's (DU_REBUILD=1 forces all).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../libdu_b200.so"
@@ -14,17 +14,20 @@ stale() {  # $1 = unit name
   local o="$HERE/_obj/$1.o"
   [ "${DU_REBUILD:-0}" = "1" ] && return 0
   [ -f "$o" ] || return 0
+  # an object built with other flags than this call's (e.g. a -DDU_PRED_DEV development build) is stale
+  [ "$(cat "$HERE/_obj/$1.flags" 2>/dev/null)" = "$EXTRA" ] || return 0
   local dep
   for dep in "$HERE/$1.cu" "$HERE"/*.cuh "$HERE"/../../include/*.h "${BASH_SOURCE[0]}"; do
     [ "$dep" -nt "$o" ] && return 0
   done
   return 1
 }
+EXTRA="$*"
 pids=()
 for f in "${SRCS[@]}"; do
   [ -f "$HERE/$f.cu" ] || continue
-  if [ $# -gt 0 ] || stale "$f"; then
-    ( "$NVCC" "${FLAGS[@]}" "$@" -o "$HERE/_obj/$f.o" "$HERE/$f.cu" > "$HERE/_obj/$f.log" 2>&1 || { rm -f "$HERE/_obj/$f.o"; exit 1; } ) &
+  if stale "$f"; then
+    ( "$NVCC" "${FLAGS[@]}" "$@" -o "$HERE/_obj/$f.o" "$HERE/$f.cu" > "$HERE/_obj/$f.log" 2>&1 && echo "$EXTRA" > "$HERE/_obj/$f.flags" || { rm -f "$HERE/_obj/$f.o"; exit 1; } ) &
     pids+=($!)
   fi
 done

@@ -77,6 +77,7 @@ __device__ __forceinline__ uint4 ldg_stream_128_at(const void* row, uint32_t byt
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int VEC = 4;
+  __device__ static __forceinline__ uint4 ld(const void* p, uint64_t pol) { return ldg_stream_128_pol(p, pol); }
   static constexpr int DT = DU_F32;
   __device__ static __forceinline__ uint4 load(const void* base, int64_t idx) {
     return ldg_stream_128(reinterpret_cast<const float*>(base) + idx);
@@ -87,6 +88,7 @@ template <> struct Vec16<float> {
 };
 template <> struct Vec16<__half> {
   static constexpr int VEC = 8;
+  __device__ static __forceinline__ uint4 ld(const void* p, uint64_t pol) { return ldg_stream_128_pol(p, pol); }
   static constexpr int DT = DU_F16;
   __device__ static __forceinline__ uint4 load(const void* base, int64_t idx) {
     return ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
@@ -102,6 +104,7 @@ template <> struct Vec16<__half> {
 };
 template <> struct Vec16<__nv_bfloat16> {
   static constexpr int VEC = 8;
+  __device__ static __forceinline__ uint4 ld(const void* p, uint64_t pol) { return ldg_stream_128_pol(p, pol); }
   static constexpr int DT = DU_BF16;
   __device__ static __forceinline__ uint4 load(const void* base, int64_t idx) {
     return ldg_stream_128(reinterpret_cast<const uint16_t*>(base) + idx);
@@ -112,6 +115,35 @@ template <> struct Vec16<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
   }
 };
+
+// 8-byte vector of a 16-bit type (4 elements): the same interface, carried in the low half of a uint4.  Used where 8
+// elements per thread cost more registers than the streaming loop has (the predictive fused step with fp16 / bf16 scores).
+__device__ __forceinline__ uint4 ldg_stream_64_pol(const void* p, uint64_t pol) {
+  uint4 r;
+  r.z = 0u; r.w = 0u;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(pol));
+  return r;
+}
+template <typename T> struct Vec8;
+template <> struct Vec8<__half> {
+  static constexpr int VEC = 4;
+  static constexpr int DT = DU_F16;
+  __device__ static __forceinline__ uint4 ld(const void* p, uint64_t pol) { return ldg_stream_64_pol(p, pol); }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __half2float(__ushort_as_half((unsigned short)(r.x & 0xffff))); v[1] = __half2float(__ushort_as_half((unsigned short)(r.x >> 16)));
+    v[2] = __half2float(__ushort_as_half((unsigned short)(r.y & 0xffff))); v[3] = __half2float(__ushort_as_half((unsigned short)(r.y >> 16)));
+  }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static constexpr int VEC = 4;
+  static constexpr int DT = DU_BF16;
+  __device__ static __forceinline__ uint4 ld(const void* p, uint64_t pol) { return ldg_stream_64_pol(p, pol); }
+  __device__ static __forceinline__ void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
+template <> struct Vec8<float> : Vec16<float> {};   // (never narrower than 16 bytes for fp32)
 
 // Shifted-data accumulation of one batch of score vectors (SURVEY.md §7 "Variance numerics"): d = x - k with
 // k the first sample (variance modes) or the centre; s1 = sum d, s2 = sum d^2.
@@ -166,17 +198,16 @@ __device__ __forceinline__ void accumulate_scores(const void* const* scores, int
 // Same contract as accumulate_scores with M known at compile time: no predication, every load of a batch (<= 8 score
 // vectors + the centre) is issued before the first use.
 // HINT: the score loads carry the L2 eviction policy `pol` (see ldg_stream_128_pol)
-template <typename T, int MT, bool HINT = false>
+template <typename T, int MT, bool HINT = false, typename V = Vec16<T>>
 __device__ __forceinline__ void accumulate_scores_ct(const void* const* scores, int64_t row_off, uint32_t byte_off, const uint4& raw_c,
                                                      int centre_mode, bool c_ready, bool shift_first,
-                                                     float (&c)[Vec16<T>::VEC], float (&k)[Vec16<T>::VEC],
-                                                     float (&s1)[Vec16<T>::VEC], float (&s2)[Vec16<T>::VEC], uint64_t pol = 0) {
-  using V = Vec16<T>;
+                                                     float (&c)[V::VEC], float (&k)[V::VEC],
+                                                     float (&s1)[V::VEC], float (&s2)[V::VEC], uint64_t pol = 0) {
   constexpr int VEC = V::VEC;
   constexpr int BATCH = (MT <= 8) ? MT : 8;
   auto load = [&](int m) -> uint4 {
     const char* ptr = reinterpret_cast<const char*>(reinterpret_cast<const T*>(scores[m]) + row_off) + byte_off;
-    if constexpr (HINT) return ldg_stream_128_pol(ptr, pol);
+    if constexpr (HINT) return V::ld(ptr, pol);
     else return ldg_stream_128(ptr);
   };
   uint4 raw[BATCH];

@@ -1,5 +1,6 @@
 // du_fused_pred.cu — the predictive single-pass fused uncertainty step (see the block comment below).
 #include <cmath>
+#include <type_traits>
 
 #include "du_fused.cuh"
 
@@ -57,9 +58,12 @@ __device__ __forceinline__ void guided_elem(const du_ddim_coeffs& dc, float post
 
 // OUTS: some of the optional outputs (x0, guided eps, mask) are requested; the common launch writes x_{t-1} only and keeps
 // none of those values alive in the (register-bound) streaming loop.
-template <typename T, int MT, int THREADS, int MINB, bool OUTS>
+// NARROW: 16-bit scores are read as 8-byte vectors (4 elements per thread and trip, like fp32) instead of 16-byte ones: the
+// loop then has the register budget and the trip count of the fp32 instance (8 elements per thread spilled and left only 6
+// trips, below the point where the single pass pays).
+template <typename T, int MT, int THREADS, int MINB, bool OUTS, bool NARROW>
 __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_constant__ PredKParams pk) {
-  using FV = Vec16<T>;
+  using FV = typename std::conditional<NARROW, Vec8<T>, Vec16<T>>::type;
   constexpr int VEC = FV::VEC;
   constexpr int LOW = H1_BITS + H2_BITS;
   const FusedKParams& kp = pk.k;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       const uint32_t byte_off = g_elems * (uint32_t)sizeof(T);
       // eps was just read by du_batch_sum (evict-last): it comes from L2.  The pilot reads its rows once more later (normal
       // priority); every other read is the last one and, like the scores and the sample, asks to be evicted first.
-      const uint4 raw_e = ldg_stream_128_pol(reinterpret_cast<const char*>(eps_row) + byte_off, pilot_only ? kL2EvictNormal : pol);
+      const uint4 raw_e = FV::ld(reinterpret_cast<const char*>(eps_row) + byte_off, pilot_only ? kL2EvictNormal : pol);
       uint4 raw_s[VEC / 4];
       float4 raw_S[VEC / 4];
       if (!pilot_only) {
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       }
       if (from_scores) {
         float c[VEC], k[VEC], s1[VEC], s2[VEC];
-        if constexpr (MT > 0) accumulate_scores_ct<T, MT, true>(p.scores, srow, byte_off, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2, pol);
+        if constexpr (MT > 0) accumulate_scores_ct<T, MT, true, FV>(p.scores, srow, byte_off, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2, pol);
         else accumulate_scores<T>(p.scores, p.M, srow + g_elems, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2);
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
@@ -363,9 +367,12 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
 
 static constexpr size_t kPredFixedBytes = (size_t)(H0_WORDS + PRED_WORK_WORDS + MISC_WORDS) * 4;
 
+template <typename T, int MT>
+constexpr bool pred_narrow() { return sizeof(T) == 2 && MT > 0; }
+
 template <typename T, int MT, int THREADS, int MINB, bool OUTS>
 static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t smem, cudaStream_t st) {
-  auto kern = fused_pred_kernel<T, MT, THREADS, MINB, OUTS>;
+  auto kern = fused_pred_kernel<T, MT, THREADS, MINB, OUTS, pred_narrow<T, MT>()>;
   static size_t smem_set[64] = {0};
   int dev = 0;
   DU_CUDA(cudaGetDevice(&dev));
@@ -436,7 +443,10 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
   const bool fast_c = p.ddim.prediction_type == DU_PRED_EPSILON && !p.ddim.use_clipped_model_output &&
                       p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32;
   if (!fast_c || (plan.threads != 512 && plan.threads != 1024)) return 0;
-  const int vec = p.score_dtype == DU_F32 ? 4 : 8;
+  // elements per thread and trip: 4, except 16-bit scores with a runtime-M instance (16-byte vectors of 8)
+  const bool outs_req = p.x0_out || p.eps_out || p.mask_out;
+  const bool mt_known = outs_req ? (p.M == 5) : (p.M == 4 || p.M == 5 || p.M == 8 || p.M == 16);   // mirrors launch_pred
+  const int vec = (p.score_dtype == DU_F32 || mt_known) ? 4 : 8;
   const int64_t L = kp.L, ngroups = L / vec;
   if (L >= 65536) return 0;   // packed 16-bit level-0 counters
   // Threads per CTA: the plan's (512 x 2 CTAs or 1024 x 1 per SM, 64 registers).  384 / 768 threads with 80 registers keep
