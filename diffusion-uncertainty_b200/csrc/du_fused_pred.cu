@@ -412,9 +412,12 @@ static int launch_pred_m(const PredKParams& pk, const FusedPlan& plan, int threa
 #else
   switch (threads) {
     case 1024: return launch_pred_t<T, MT, 1024, 1, OUTS>(pk, plan, smem, st);
+#ifdef DU_PRED_TUNING   // 384 / 768-thread CTAs (80 registers): measured slower, kept for sweeps only (csrc/build.sh -DDU_PRED_TUNING)
     case 768: return launch_pred_t<T, MT, 768, 1, OUTS>(pk, plan, smem, st);
     case 384: return launch_pred_t<T, MT, 384, 2, OUTS>(pk, plan, smem, st);
-    default: return launch_pred_t<T, MT, 512, 2, OUTS>(pk, plan, smem, st);
+#endif
+    case 512: return launch_pred_t<T, MT, 512, 2, OUTS>(pk, plan, smem, st);
+    default: return 0;
   }
 #endif
 }
