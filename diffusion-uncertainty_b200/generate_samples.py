@@ -38,6 +38,19 @@ def generate_samples_model_scheduler_class_conditioned_from_tensor(X_T: torch.Te
                                                                    device: torch.device, model: torch.nn.Module, scheduler,
                                                                    fid_evaluator: Any = None, save_intermediates: bool = False):
     assert X_T.shape[0] == y.shape[0], f"{X_T.shape=} {y.shape=}"
+    return _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned=True)
+
+
+@torch.no_grad()
+def generate_samples_model_scheduler_unconditioned_from_tensor(X_T: torch.Tensor, batch_size: int, device: torch.device,
+                                                               model: torch.nn.Module, scheduler, fid_evaluator: Any = None,
+                                                               save_intermediates: bool = False):
+    """Drop-in for the unconditioned (CIFAR-10 DDPM) loop, generate_samples.py:366-463: the model is called as
+    `model(x, t).sample[:, :3]` (:414), no class labels, no `scale_model_input`; outputs and accumulation as above."""
+    return _sampling_loop(X_T, None, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned=False)
+
+
+def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned: bool):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError(f"device {device}: the uncertainty path has no CPU fallback")
@@ -52,12 +65,13 @@ def generate_samples_model_scheduler_class_conditioned_from_tensor(X_T: torch.Te
     while start < num_samples:
         stop = min(start + batch_size, num_samples)
         x = X_T[start:stop].to(device)
-        y_batch = y[start:stop].to(device)
+        y_batch = y[start:stop].to(device) if conditioned else None
         B = stop - start
         scheduler.set_timesteps(n_steps)
         acc_u = acc_s = None
         if with_unc:
-            scheduler.prompt_embeds = y_batch
+            if conditioned:
+                scheduler.prompt_embeds = y_batch
             t_uc = len(scheduler.uncertainty_timesteps()) if hasattr(scheduler, "uncertainty_timesteps") else sum(
                 1 for t in scheduler.timesteps.tolist() if scheduler.timestep_after_step >= t >= scheduler.timestep_end_step)
             if t_uc > 0:
@@ -72,8 +86,11 @@ def generate_samples_model_scheduler_class_conditioned_from_tensor(X_T: torch.Te
         try:
             for t in scheduler.timesteps.tolist():
                 t_tensor = torch.full((B,), t, device=device, dtype=torch.long)
-                x = scheduler.scale_model_input(x, t)
-                noisy_residual = predict_model(model, x, t_tensor, y_batch)
+                if conditioned:
+                    x = scheduler.scale_model_input(x, t)
+                    noisy_residual = predict_model(model, x, t_tensor, y_batch)
+                else:
+                    noisy_residual = model(x, t_tensor).sample[:, :3]
                 output = scheduler.step(noisy_residual, t, x)
                 if save_intermediates:
                     inter.append(output.prev_sample)

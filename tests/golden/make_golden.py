@@ -269,8 +269,30 @@ def main_dpm():
                        cfg_over=dict(variance_type="fixed_small", timestep_spacing="trailing", beta_schedule="scaled_linear"))
 
 
+def main_uncond():
+    """The unconditioned (CIFAR-10) L4 loop, generate_samples.py:366-463, with the Cifar10 scheduler class of
+    `uncertainty_centered` (the zig-zag module of the reference has no Cifar10 class).  `python tests/golden/make_golden.py uncond`."""
+    import diffusion_uncertainty.generate_samples as gs
+    from tests.toy_models import ToyUNet2D3
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    mod = __import__(SU + "scheduling_ddim_uncertainty_centered", fromlist=["x"])
+    model = ToyUNet2D3(3, seed=30).eval()
+    g = torch.Generator().manual_seed(130)
+    x_T = torch.randn(5, 3, 16, 16, generator=g)
+    with quiet():
+        sched = mod.DDIMSchedulerUncertaintyCifar10.from_config(base_config(), unet=model, M=3, after_step=14, num_steps_uc=5)
+        sched.set_timesteps(20)
+        with seeded_noise(78):
+            res = gs.generate_samples_model_scheduler_unconditioned_from_tensor(
+                X_T=x_T, batch_size=2, device=torch.device("cpu"), model=model, scheduler=sched)
+    save("l4_unconditioned", x_T=x_T, gen_images=res["gen_images"], uncertainty=res["uncertainty"], score=res["score"])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "dpm":
+    if len(sys.argv) > 1 and sys.argv[1] == "uncond":
+        main_uncond()
+    elif len(sys.argv) > 1 and sys.argv[1] == "dpm":
         main_dpm()
     elif len(sys.argv) > 1 and sys.argv[1] == "widen":
         main_widen()

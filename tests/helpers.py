@@ -29,3 +29,26 @@ def l4_sampling_loop(scheduler, model, x_T, y, eta=0.0, slice_channels=None):
         "score": torch.stack(scores, dim=1) if scores else None,
         "prevs": prevs,
     }
+
+
+def l4_unconditioned_loop(scheduler, model, X_T, batch_size):
+    """The reference's unconditioned loop restated (diffusion_uncertainty/generate_samples.py:366-463): batches of X_T,
+    `model(x, t).sample[:, :3]`, scheduler.step, per-step maps / scores stacked on dim 1, uint8 epilogue."""
+    imgs, uncs, scores = [], [], []
+    with torch.no_grad():
+        for a in range(0, X_T.shape[0], batch_size):
+            x = X_T[a:a + batch_size]
+            u_b, s_b = [], []
+            for t in scheduler.timesteps:
+                t = int(t.item())
+                t_tensor = torch.full((x.shape[0],), t, device=x.device, dtype=torch.long)
+                eps = model(x, t_tensor).sample[:, :3]
+                out = scheduler.step(eps, t, x)
+                if scheduler.timestep_after_step >= t >= scheduler.timestep_end_step:
+                    u_b.append(out.uncertainty.cpu())
+                    s_b.append(out.pred_epsilon.cpu())
+                x = out.prev_sample
+            uncs.append(torch.stack(u_b, dim=1))
+            scores.append(torch.stack(s_b, dim=1))
+            imgs.append(((x / 2 + 0.5).clamp(0, 1) * 255.0).round().to(torch.uint8))
+    return {"gen_images": torch.cat(imgs, 0).cpu(), "uncertainty": torch.cat(uncs, 0), "score": torch.cat(scores, 0)}

@@ -101,6 +101,22 @@ def test_oracle_dpm2_scheduler_matches_reference(golden_dir, case):
     assert same(res["final"].numpy(), g["final"])
 
 
+def test_oracle_unconditioned_loop_matches_reference(golden_dir):
+    """generate_samples_model_scheduler_unconditioned_from_tensor (generate_samples.py:366-463) with the Cifar10 class of
+    `uncertainty_centered`: oracle scheduler + restated loop, bit for bit"""
+    from tests.helpers import l4_unconditioned_loop
+    from tests.toy_models import ToyUNet2D3
+    g = load(golden_dir, "l4_unconditioned")
+    model = ToyUNet2D3(3, seed=30).eval()
+    sched = O.OracleScheduler("centered", None, unet=model, M=3, after_step=14, num_steps_uc=5)
+    sched.predict = lambda x, t: model(x, t).sample
+    sched.set_timesteps(20)
+    with seeded_noise(78):
+        res = l4_unconditioned_loop(sched, model, T(g["x_T"]), 2)
+    assert same(res["gen_images"].numpy(), g["gen_images"])
+    assert same(res["uncertainty"].numpy(), g["uncertainty"]) and same(res["score"].numpy(), g["score"])
+
+
 def test_quantile_restatement_is_torch_quantile(golden_dir):
     g = load(golden_dir, "threshold_map")
     for tag in "abcdef":

@@ -239,6 +239,24 @@ def test_generate_samples_loop_matches_the_reference_loop(golden_dir):
     assert sched.map_sink is None
 
 
+def test_unconditioned_loop_matches_the_reference_loop(golden_dir):
+    """the CIFAR-10 style loop (generate_samples.py:366-463): `model(x, t).sample[:, :3]`, Cifar10 scheduler class"""
+    import diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim_uncertainty_centered as mod
+    from diffusion_uncertainty_b200.generate_samples import generate_samples_model_scheduler_unconditioned_from_tensor as gen
+    from tests.toy_models import ToyUNet2D3
+    g = load(golden_dir, "l4_unconditioned")
+    model = ToyUNet2D3(3, seed=30).eval().to(dev())
+    sched = mod.DDIMSchedulerUncertaintyCifar10.from_config(
+        dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True, set_alpha_to_one=True,
+             steps_offset=0, prediction_type="epsilon", timestep_spacing="leading"), unet=model, M=3, after_step=14, num_steps_uc=5)
+    sched.set_timesteps(20)
+    with seeded_noise(78):
+        res = gen(X_T=T(g["x_T"]), batch_size=2, device=dev(), model=model, scheduler=sched)
+    assert res["gen_images"].dtype == torch.uint8 and same(res["gen_images"].numpy(), g["gen_images"])
+    assert same(res["score"].numpy(), g["score"])
+    assert res["uncertainty"].shape == g["uncertainty"].shape and rel_close(res["uncertainty"], g["uncertainty"], 1e-5, atol=1e-12)
+
+
 def test_accumulator_slots_and_async_copy():
     from diffusion_uncertainty_b200 import ops
     from diffusion_uncertainty_b200.accumulate import UncertaintyMapAccumulator

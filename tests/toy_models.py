@@ -99,3 +99,23 @@ class ToySDUNet(torch.nn.Module):
             e = encoder_hidden_states.float().reshape(encoder_hidden_states.shape[0], -1)[:, :1]
             h = h + (e * 0.25).view(-1, 1, 1, 1)
         return (h.clamp(-3.0, 3.0),)
+
+
+class _SampleOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+
+class ToyUNet2D(ToyADM):
+    """diffusers-UNet2DModel-shaped stand-in for the unconditioned (CIFAR-10) loop: `model(x, t).sample` is the 6-channel
+    ToyADM output (generate_samples.py:414 slices `[:, :3]`; the Cifar10 scheduler classes call `unet(x, t).sample`)."""
+
+    def forward(self, x, t, y=None, **kw):
+        return _SampleOutput(super().forward(x, t, y=None))
+
+
+class ToyUNet2D3(ToyUNet2D):
+    """the same with a 3-channel `.sample` (what the scheduler's own forwards need: Cifar10.predict_model does not slice)"""
+
+    def forward(self, x, t, y=None, **kw):
+        return _SampleOutput(ToyADM.forward(self, x, t, y=None)[:, :3])
