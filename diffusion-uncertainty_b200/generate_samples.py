@@ -50,7 +50,20 @@ def generate_samples_model_scheduler_unconditioned_from_tensor(X_T: torch.Tensor
     return _sampling_loop(X_T, None, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned=False)
 
 
-def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned: bool):
+@torch.no_grad()
+def generate_samples_model_scheduler_class_conditioned_uvit_from_tensor(X_T: torch.Tensor, y: torch.Tensor, batch_size: int,
+                                                                        uvit_ae: torch.nn.Module, scheduler,
+                                                                        device="cpu", fid_evaluator: Any = None):
+    """Drop-in for the U-ViT latent loop, generate_samples.py:469-571: `uvit_ae(x, t, y)` on the `[B,4,h,w]` latent (no channel
+    slice), `uvit_ae.decode(x)` before the uint8 epilogue, `timestep` in the result.  (The reference's default device 'cpu'
+    is kept in the signature; this path has no CPU fallback and raises on it.)"""
+    assert X_T.shape[0] == y.shape[0], f"{X_T.shape=} {y.shape=}"
+    res = _sampling_loop(X_T, y, batch_size, device, uvit_ae, scheduler, fid_evaluator, False, conditioned=True, uvit=True)
+    return {"timestep": scheduler.timesteps, **res}
+
+
+def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned: bool,
+                   uvit: bool = False):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError(f"device {device}: the uncertainty path has no CPU fallback")
@@ -86,7 +99,9 @@ def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, 
         try:
             for t in scheduler.timesteps.tolist():
                 t_tensor = torch.full((B,), t, device=device, dtype=torch.long)
-                if conditioned:
+                if uvit:
+                    noisy_residual = model(x, t_tensor, y_batch)
+                elif conditioned:
                     x = scheduler.scale_model_input(x, t)
                     noisy_residual = predict_model(model, x, t_tensor, y_batch)
                 else:
@@ -111,6 +126,8 @@ def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, 
                 host_score = torch.empty(shape, dtype=acc_s.buffer.dtype, pin_memory=True)
             copies.append(acc_u.to_host_async(host_unc[start:stop])[1])
             copies.append(acc_s.to_host_async(host_score[start:stop])[1])
+        if uvit:
+            x = model.decode(x)               # latent -> pixels: the reference's autoencoder module (:539)
         gen = ops.image_uint8(x)          # (x/2 + .5).clamp(0,1)*255 -> round -> uint8 (:203-212), one launch
         if fid_evaluator is not None:
             fid_evaluator.update(gen, real=False)

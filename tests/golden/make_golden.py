@@ -289,8 +289,42 @@ def main_uncond():
     save("l4_unconditioned", x_T=x_T, gen_images=res["gen_images"], uncertainty=res["uncertainty"], score=res["score"])
 
 
+def main_uvit():
+    """The U-ViT latent loop, generate_samples.py:469-571 (`uvit_ae(x, t, y)`, `uvit_ae.decode` before the uint8 epilogue), with
+    a toy subclass of the reference's UViTAE so that the reference's isinstance dispatch (traits.py:12) takes the U-ViT
+    branch.  `python tests/golden/make_golden.py uvit`."""
+    import diffusion_uncertainty.generate_samples as gs
+    from diffusion_uncertainty.uvit.uvit_ae import UViTAE as RefUViTAE
+    from tests.toy_models import ToyUViTMixin
+
+    class ToyRefUViTAE(ToyUViTMixin, RefUViTAE):
+        def __init__(self, seed):
+            torch.nn.Module.__init__(self)
+            self.toy_init(seed)
+
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    mod = __import__(SU + "scheduling_ddim_uncertainty_zigzag_centered", fromlist=["x"])
+    model = ToyRefUViTAE(40).eval()
+    g = torch.Generator().manual_seed(140)
+    x_T = torch.randn(5, 4, 8, 8, generator=g)
+    y = torch.randint(0, 10, (5,), generator=g)
+    with quiet():
+        sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
+            base_config(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, clip_sample=False, set_alpha_to_one=False,
+                        steps_offset=1), unet=model, M=3, after_step=14, num_steps_uc=5, num_zigzag=2)
+        sched.set_timesteps(20)
+        with seeded_noise(79):
+            res = gs.generate_samples_model_scheduler_class_conditioned_uvit_from_tensor(
+                X_T=x_T, y=y, batch_size=2, uvit_ae=model, scheduler=sched, device=torch.device("cpu"))
+    save("l4_uvit", x_T=x_T, y=y, gen_images=res["gen_images"], uncertainty=res["uncertainty"], score=res["score"],
+         timestep=res["timestep"])
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "uncond":
+    if len(sys.argv) > 1 and sys.argv[1] == "uvit":
+        main_uvit()
+    elif len(sys.argv) > 1 and sys.argv[1] == "uncond":
         main_uncond()
     elif len(sys.argv) > 1 and sys.argv[1] == "dpm":
         main_dpm()

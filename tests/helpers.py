@@ -52,3 +52,27 @@ def l4_unconditioned_loop(scheduler, model, X_T, batch_size):
             scores.append(torch.stack(s_b, dim=1))
             imgs.append(((x / 2 + 0.5).clamp(0, 1) * 255.0).round().to(torch.uint8))
     return {"gen_images": torch.cat(imgs, 0).cpu(), "uncertainty": torch.cat(uncs, 0), "score": torch.cat(scores, 0)}
+
+
+def l4_uvit_loop(scheduler, uvit_ae, X_T, y, batch_size):
+    """The reference's U-ViT latent loop restated (diffusion_uncertainty/generate_samples.py:469-571)."""
+    imgs, uncs, scores = [], [], []
+    with torch.no_grad():
+        for a in range(0, X_T.shape[0], batch_size):
+            x, yb = X_T[a:a + batch_size], y[a:a + batch_size]
+            scheduler.prompt_embeds = yb
+            scheduler.set_timesteps(len(scheduler.timesteps))
+            u_b, s_b = [], []
+            for t in scheduler.timesteps:
+                t = int(t.item())
+                t_tensor = torch.full((yb.shape[0],), t, device=x.device, dtype=torch.long)
+                out = scheduler.step(uvit_ae(x, t_tensor, yb), t, x)
+                if scheduler.timestep_after_step >= t >= scheduler.timestep_end_step:
+                    u_b.append(out.uncertainty.cpu())
+                    s_b.append(out.pred_epsilon.cpu())
+                x = out.prev_sample
+            uncs.append(torch.stack(u_b, dim=1))
+            scores.append(torch.stack(s_b, dim=1))
+            x = uvit_ae.decode(x)
+            imgs.append(((x / 2 + 0.5).clamp(0, 1) * 255.0).round().to(torch.uint8))
+    return {"gen_images": torch.cat(imgs, 0).cpu(), "uncertainty": torch.cat(uncs, 0), "score": torch.cat(scores, 0)}

@@ -117,6 +117,27 @@ def test_oracle_unconditioned_loop_matches_reference(golden_dir):
     assert same(res["uncertainty"].numpy(), g["uncertainty"]) and same(res["score"].numpy(), g["score"])
 
 
+UVIT_CFG = dict(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, clip_sample=False, set_alpha_to_one=False,
+                steps_offset=1)
+
+
+def test_oracle_uvit_loop_matches_reference(golden_dir):
+    """generate_samples_model_scheduler_class_conditioned_uvit_from_tensor (generate_samples.py:469-571), U-ViT scheduler
+    config of uvit/load_pretrained_models.py:45-57: oracle scheduler + restated loop, bit for bit"""
+    from tests.helpers import l4_uvit_loop
+    from tests.toy_models import UViTAE
+    g = load(golden_dir, "l4_uvit")
+    model = UViTAE(40).eval()
+    sched = O.OracleScheduler("zigzag_centered", None, unet=model, M=3, after_step=14, num_steps_uc=5, num_zigzag=2, **UVIT_CFG)
+    sched.predict = lambda x, t: model(x, t if torch.is_tensor(t) else torch.full((x.shape[0],), int(t)), sched.prompt_embeds)
+    sched.set_timesteps(20)
+    assert same(sched.timesteps.numpy(), g["timestep"])
+    with seeded_noise(79):
+        res = l4_uvit_loop(sched, model, T(g["x_T"]), T(g["y"]), 2)
+    assert same(res["gen_images"].numpy(), g["gen_images"])
+    assert same(res["uncertainty"].numpy(), g["uncertainty"]) and same(res["score"].numpy(), g["score"])
+
+
 def test_quantile_restatement_is_torch_quantile(golden_dir):
     g = load(golden_dir, "threshold_map")
     for tag in "abcdef":

@@ -257,6 +257,28 @@ def test_unconditioned_loop_matches_the_reference_loop(golden_dir):
     assert res["uncertainty"].shape == g["uncertainty"].shape and rel_close(res["uncertainty"], g["uncertainty"], 1e-5, atol=1e-12)
 
 
+def test_uvit_loop_matches_the_reference_loop(golden_dir):
+    """the U-ViT latent loop (generate_samples.py:469-571): positional class label, 4-channel latent, decode before uint8"""
+    import diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim_uncertainty_zigzag_centered as mod
+    from diffusion_uncertainty_b200.generate_samples import generate_samples_model_scheduler_class_conditioned_uvit_from_tensor as gen
+    from tests.test_oracle_golden import UVIT_CFG
+    from tests.toy_models import UViTAE
+    g = load(golden_dir, "l4_uvit")
+    model = UViTAE(40).eval().to(dev())
+    sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
+        {**dict(num_train_timesteps=1000, prediction_type="epsilon", timestep_spacing="leading"), **UVIT_CFG},
+        unet=model, M=3, after_step=14, num_steps_uc=5, num_zigzag=2)
+    sched.set_timesteps(20)
+    with seeded_noise(79):
+        res = gen(X_T=T(g["x_T"]), y=T(g["y"]), batch_size=2, uvit_ae=model, scheduler=sched, device=dev())
+    assert same(res["timestep"].cpu().numpy(), g["timestep"])
+    assert res["gen_images"].shape == g["gen_images"].shape and same(res["gen_images"].numpy(), g["gen_images"])
+    assert same(res["score"].numpy(), g["score"])
+    assert rel_close(res["uncertainty"], g["uncertainty"], 1e-5, atol=1e-12)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gen(X_T=T(g["x_T"]), y=T(g["y"]), batch_size=2, uvit_ae=model, scheduler=sched)      # the reference's default device
+
+
 def test_accumulator_slots_and_async_copy():
     from diffusion_uncertainty_b200 import ops
     from diffusion_uncertainty_b200.accumulate import UncertaintyMapAccumulator

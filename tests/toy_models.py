@@ -119,3 +119,35 @@ class ToyUNet2D3(ToyUNet2D):
 
     def forward(self, x, t, y=None, **kw):
         return _SampleOutput(ToyADM.forward(self, x, t, y=None)[:, :3])
+
+
+class ToyUViTMixin:
+    """U-ViT-with-autoencoder-shaped stand-in: `model(z[B,4,h,w], t[B], y[B]) -> [B,4,h,w]` (class label positional, no channel
+    slice: traits.py:12-13) and `decode(z) -> [B,3,2h,2w]`.  Mixed into a class NAMED UViTAE (the drop-in dispatches on the
+    class name) or into a subclass of the reference's UViTAE (tests/golden/make_golden.py)."""
+
+    def toy_init(self, seed: int = 0):
+        g = torch.Generator().manual_seed(seed)
+        self.register_buffer("ta", torch.randn(4, 1, 1, generator=g) * 0.5)
+        self.register_buffer("tb", torch.randn(4, 1, 1, generator=g) * 0.25)
+        self.register_buffer("tc", torch.randn(4, 1, 1, generator=g) * 0.5)
+        self.register_buffer("td", torch.randn(4, 1, 1, generator=g) * 0.125)
+        self.register_buffer("dec", torch.randn(3, 4, 1, 1, generator=g) * 0.5)
+
+    def forward(self, x, t, y=None, **kw):
+        x = x.float()
+        h = self.ta * x + self.tb * (torch.roll(x, 1, -1) * torch.roll(x, 1, -2))
+        h = h + self.tc * (t.float() * (1.0 / 1024.0)).view(-1, 1, 1, 1)
+        if y is not None:
+            h = h + self.td * (y.float() * 0.125).view(-1, 1, 1, 1)
+        return h.clamp(-3.0, 3.0)
+
+    def decode(self, z):
+        img = (self.dec.unsqueeze(0) * z.float().unsqueeze(1)).sum(dim=2)          # 1x1 mix of the 4 latent channels -> 3
+        return torch.repeat_interleave(torch.repeat_interleave(img, 2, dim=-1), 2, dim=-2)
+
+
+class UViTAE(ToyUViTMixin, torch.nn.Module):
+    def __init__(self, seed: int = 0):
+        torch.nn.Module.__init__(self)
+        self.toy_init(seed)
