@@ -62,8 +62,48 @@ def generate_samples_model_scheduler_class_conditioned_uvit_from_tensor(X_T: tor
     return {"timestep": scheduler.timesteps, **res}
 
 
+@torch.no_grad()
+def generate_samples_model_scheduler_class_conditioned(num_samples: int, batch_size: int, image_size: int, model: torch.nn.Module,
+                                                       scheduler, num_classes, device=None, fid_evaluator: Any = None,
+                                                       init_seed_rng: int = 0, is_uvit: bool = False, skip_seed: int = 1,
+                                                       is_cifar10: bool = False):
+    """Drop-in for the seed-driven loop, generate_samples.py:18-125 (scripts/compute_fid_imagenet.py:139): batch k starts from
+    `torch.randn(batch_size, C, S, S, generator=Generator(device).manual_seed(init_seed_rng + k * skip_seed))` and, for an
+    integer `num_classes`, labels drawn from the same re-seeded generator; a label TENSOR fixes the labels and truncates the
+    last batch.  Whole batches are generated (an integer `num_classes` never truncates), `x_t` keeps the untruncated draws —
+    both as in the reference.  Model call: `model(x, t, y=y)[:, :3]`, `model(x, t, y)` (is_uvit, + decode) or
+    `model(x, t).sample` (is_cifar10).  Returns y, x_t, timestep, gen_images (+ uncertainty, score, fid)."""
+    device = torch.device(device if device is not None else "cpu")
+    if device.type != "cuda":
+        raise RuntimeError(f"device {device}: the uncertainty path has no CPU fallback")
+    generator = torch.Generator(device=device)
+    channels = 4 if is_uvit else 3
+    starts, labels, raw = [], [], []
+    generated, k = 0, 0
+    while num_samples > generated:
+        seed = init_seed_rng + k * skip_seed
+        x = torch.randn(batch_size, channels, image_size, image_size, device=device, dtype=torch.float32,
+                        generator=generator.manual_seed(seed))
+        raw.append(x.cpu().clone())
+        if isinstance(num_classes, int):
+            yb = torch.randint(0, num_classes, (batch_size,), device=device, generator=generator.manual_seed(seed))
+        else:
+            assert num_samples == num_classes.shape[0]
+            yb = num_classes[generated:generated + batch_size]
+            if yb.shape[0] < batch_size:
+                x = x[:yb.shape[0]]
+        starts.append(x)
+        labels.append(yb)
+        generated += x.shape[0]
+        k += 1
+    y_all = torch.cat(labels, dim=0)
+    res = _sampling_loop(torch.cat(starts, dim=0), y_all, batch_size, device, model, scheduler, fid_evaluator, False,
+                         conditioned=True, uvit=is_uvit, sample_attr=is_cifar10)
+    return {"y": y_all.cpu(), "x_t": torch.cat(raw, dim=0), "timestep": scheduler.timesteps, **res}
+
+
 def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, save_intermediates, conditioned: bool,
-                   uvit: bool = False):
+                   uvit: bool = False, sample_attr: bool = False):
     device = torch.device(device)
     if device.type != "cuda":
         raise RuntimeError(f"device {device}: the uncertainty path has no CPU fallback")
@@ -101,6 +141,8 @@ def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, 
                 t_tensor = torch.full((B,), t, device=device, dtype=torch.long)
                 if uvit:
                     noisy_residual = model(x, t_tensor, y_batch)
+                elif sample_attr:
+                    noisy_residual = model(x, t_tensor).sample            # (:71, no channel slice)
                 elif conditioned:
                     x = scheduler.scale_model_input(x, t)
                     noisy_residual = predict_model(model, x, t_tensor, y_batch)

@@ -279,6 +279,32 @@ def test_uvit_loop_matches_the_reference_loop(golden_dir):
         gen(X_T=T(g["x_T"]), y=T(g["y"]), batch_size=2, uvit_ae=model, scheduler=sched)      # the reference's default device
 
 
+def test_seed_driven_loop_equals_the_from_tensor_loop():
+    """generate_samples.py:18-125: per-batch re-seeded starting noise and labels, whole batches, then the same loop"""
+    from diffusion_uncertainty_b200.generate_samples import (generate_samples_model_scheduler_class_conditioned as gen_seeded,
+                                                              generate_samples_model_scheduler_class_conditioned_from_tensor as gen)
+    sched, model = build(SCHED_CASES[2])
+    torch.manual_seed(3)
+    res = gen_seeded(5, 2, 16, model, sched, 10, device=dev(), init_seed_rng=7, skip_seed=3)
+    assert res["x_t"].shape == (6, 3, 16, 16) and res["y"].shape == (6,) and res["gen_images"].shape == (6, 3, 16, 16)   # whole batches
+    gg = torch.Generator(device=dev())
+    for k in range(3):
+        want = torch.randn(2, 3, 16, 16, device=dev(), generator=gg.manual_seed(7 + 3 * k))
+        assert torch.equal(res["x_t"][2 * k:2 * k + 2], want.cpu())
+        assert torch.equal(res["y"][2 * k:2 * k + 2], torch.randint(0, 10, (2,), device=dev(), generator=gg.manual_seed(7 + 3 * k)).cpu())
+    assert torch.equal(res["timestep"], sched.timesteps)
+    torch.manual_seed(3)
+    ref = gen(X_T=res["x_t"], y=res["y"], batch_size=2, device=dev(), model=model, scheduler=sched)
+    for key in ("gen_images", "uncertainty", "score"):
+        assert torch.equal(res[key], ref[key]), key
+    # a label tensor fixes the labels and truncates the last batch; x_t keeps the untruncated draws
+    labels = torch.arange(5, device=dev()) % 10
+    res2 = gen_seeded(5, 2, 16, model, sched, labels, device=dev(), init_seed_rng=7, skip_seed=3)
+    assert res2["gen_images"].shape[0] == 5 and res2["y"].tolist() == [0, 1, 2, 3, 4] and res2["x_t"].shape[0] == 6
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gen_seeded(2, 2, 16, model, sched, 10)
+
+
 def test_accumulator_slots_and_async_copy():
     from diffusion_uncertainty_b200 import ops
     from diffusion_uncertainty_b200.accumulate import UncertaintyMapAccumulator
