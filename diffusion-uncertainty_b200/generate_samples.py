@@ -73,11 +73,26 @@ def generate_samples_model_scheduler_class_conditioned(num_samples: int, batch_s
     last batch.  Whole batches are generated (an integer `num_classes` never truncates), `x_t` keeps the untruncated draws —
     both as in the reference.  Model call: `model(x, t, y=y)[:, :3]`, `model(x, t, y)` (is_uvit, + decode) or
     `model(x, t).sample` (is_cifar10).  Returns y, x_t, timestep, gen_images (+ uncertainty, score, fid)."""
+    return _seeded_loop(num_samples, batch_size, 4 if is_uvit else 3, image_size, model, scheduler, num_classes, device, fid_evaluator,
+                        init_seed_rng, skip_seed, is_uvit, is_cifar10)
+
+
+@torch.no_grad()
+def generate_samples_model_scheduler_class_conditioned_uvit(num_samples: int, batch_size: int, image_size: int, uvit_ae: torch.nn.Module,
+                                                            scheduler, num_classes, device="cpu", fid_evaluator: Any = None,
+                                                            init_seed_rng: int = 0):
+    """Drop-in for the seed-driven U-ViT loop, generate_samples.py:573-668: the latent shape comes from `uvit_ae.in_chans` /
+    `uvit_ae.img_size` (the `image_size` argument is unused there too), batch k is seeded with `init_seed_rng + k`."""
+    return _seeded_loop(num_samples, batch_size, uvit_ae.in_chans, uvit_ae.img_size, uvit_ae, scheduler, num_classes, device,
+                        fid_evaluator, init_seed_rng, 1, True, False)
+
+
+def _seeded_loop(num_samples, batch_size, channels, image_size, model, scheduler, num_classes, device, fid_evaluator, init_seed_rng,
+                 skip_seed, is_uvit, is_cifar10):
     device = torch.device(device if device is not None else "cpu")
     if device.type != "cuda":
         raise RuntimeError(f"device {device}: the uncertainty path has no CPU fallback")
     generator = torch.Generator(device=device)
-    channels = 4 if is_uvit else 3
     starts, labels, raw = [], [], []
     generated, k = 0, 0
     while num_samples > generated:

@@ -303,6 +303,26 @@ def test_seed_driven_loop_equals_the_from_tensor_loop():
     assert res2["gen_images"].shape[0] == 5 and res2["y"].tolist() == [0, 1, 2, 3, 4] and res2["x_t"].shape[0] == 6
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         gen_seeded(2, 2, 16, model, sched, 10)
+    # the U-ViT form (:573-668): latent shape from the model's attributes, seeds init + k, decode before the epilogue
+    import diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim_uncertainty_zigzag_centered as mod
+    from diffusion_uncertainty_b200.generate_samples import (generate_samples_model_scheduler_class_conditioned_uvit as gen_uvit,
+                                                              generate_samples_model_scheduler_class_conditioned_uvit_from_tensor as gen_uvit_t)
+    from tests.test_oracle_golden import UVIT_CFG
+    from tests.toy_models import UViTAE
+    ae = UViTAE(41).eval().to(dev())
+    ae.in_chans, ae.img_size = 4, 8
+    s2 = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
+        {**dict(num_train_timesteps=1000, prediction_type="epsilon", timestep_spacing="leading"), **UVIT_CFG},
+        unet=ae, M=2, after_step=6, num_steps_uc=3, num_zigzag=2)
+    s2.set_timesteps(10)
+    torch.manual_seed(4)
+    ru = gen_uvit(4, 2, 999, ae, s2, 10, device=dev(), init_seed_rng=5)
+    assert ru["x_t"].shape == (4, 4, 8, 8) and ru["gen_images"].shape == (4, 3, 16, 16)
+    assert torch.equal(ru["x_t"][2:], torch.randn(2, 4, 8, 8, device=dev(), generator=gg.manual_seed(6)).cpu())
+    torch.manual_seed(4)
+    rt = gen_uvit_t(X_T=ru["x_t"], y=ru["y"], batch_size=2, uvit_ae=ae, scheduler=s2, device=dev())
+    for key in ("gen_images", "uncertainty", "score"):
+        assert torch.equal(ru[key], rt[key]), key
 
 
 def test_accumulator_slots_and_async_copy():
