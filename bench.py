@@ -530,6 +530,9 @@ LOOPS = {
     # name: (feeder factory, total batch, C, H, betas, scheduler kwargs, generation steps)
     "imagenet128_adm_loop": ("adm_imagenet128", 128, 3, 128, dict(beta_start=1e-4, beta_end=0.02, beta_schedule="linear"),
                              dict(M=5, after_step=40, num_steps_uc=10, num_zigzag=3), 50),
+    # BASELINE.json configs[1]: ImageNet-64 ADM (dropout 0.5, cosine schedule: init_model.py:45-47, 134-137), same window
+    "imagenet64_adm_loop": ("adm_imagenet64", 128, 3, 64, dict(beta_schedule="squaredcos_cap_v2"),
+                            dict(M=5, after_step=40, num_steps_uc=10, num_zigzag=3), 50),
 }
 
 
@@ -617,13 +620,14 @@ def run_loop(args):
         ms_per_loop = ms / steps
         unc = res["uncertainty"]
         line = {
-            "metric": "imagenet128_m5_sampling_loop_throughput", "value": B_total / (ms_per_loop * 1e-3), "unit": "img/s",
+            "metric": "imagenet%d_m5_sampling_loop_throughput" % H, "value": B_total / (ms_per_loop * 1e-3), "unit": "img/s",
             "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_loop, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16 autocast (model) / f32 (uncertainty path)", "data": "synthetic",
             "config": {"workload": args.workload, "global_batch": B_total, "batch_per_gpu": B, "generation_steps": n_steps,
                        "start_step_uc": skw["after_step"], "num_steps_uc": skw["num_steps_uc"], "M": skw["M"],
                        "num_zigzag": skw["num_zigzag"], "scheduler": "uncertainty_zigzag_centered",
-                       "model": "random-init ADM-128-shaped feeder (tools/adm_feeder.py, 421.5 M parameters)",
+                       "model": "random-init ADM-%d-shaped feeder (tools/adm_feeder.py, %.1f M parameters)"
+                                % (H, sum(p.numel() for p in model.parameters()) / 1e6),
                        "parallelism": f"batch-sharded x{world}, no collective", "step": "one full sampling loop of the batch"},
             "model_forwards_per_loop": n_fwd, "model_forward_ms": fwd_ms,
             "model_share_of_loop": n_fwd * fwd_ms / ms_per_loop,
