@@ -24,7 +24,7 @@ ZN_BELOW, ZN_ABOVE, ZN_MULTISCALE = range(3)
 # du_prediction_type
 PRED_EPSILON, PRED_SAMPLE, PRED_V = range(3)
 # du_guidance
-GUIDE_NONE, GUIDE_POSTERIOR, GUIDE_GRAD_BLEND, GUIDE_GRAD_ADD, GUIDE_WEIGHTS, GUIDE_LINCOMB = range(6)
+GUIDE_NONE, GUIDE_POSTERIOR, GUIDE_GRAD_BLEND, GUIDE_GRAD_ADD, GUIDE_WEIGHTS, GUIDE_LINCOMB, GUIDE_SIGN_ADD, GUIDE_MUL_BLEND = range(8)
 
 i64, i32, f32, vp, sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
 
@@ -69,6 +69,7 @@ class FusedParams(C.Structure):
         ("x0_out", vp), ("x0_stride", i64),
         ("eps_out", vp), ("eps_out_stride", i64),
         ("mask_out", vp), ("mask_out_stride", i64),
+        ("skip_ddim", i32), ("_reserved0", i32),
     ]
 
 
@@ -94,6 +95,8 @@ PROTOTYPES = {
     "du_guided_step": (C.c_int, [C.POINTER(GuidedParams), vp]),
     "du_batch_sum": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, vp]),
     "du_perturb": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, f32, f32, i64, i64, vp, i64, C.c_int, vp]),
+    "du_perturb_rows": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, vp, vp, i64, i64, vp, i64, C.c_int, vp]),
+    "du_ema_update": (C.c_int, [vp, vp, C.c_int, f32, f32, f32, i64, vp, vp, vp, vp]),
     "du_accumulate_slot": (C.c_int, [vp, i64, C.c_int, i64, i64, vp, i64, C.c_int, vp]),
     "du_dpm_solver_update": (C.c_int, [vp, i64, C.c_int, vp, i64, C.c_int, vp, i64, C.c_int, f32, f32, f32, f32, i64, i64, vp, i64,
                                        C.c_int, vp]),

@@ -38,6 +38,21 @@ class UncertaintyMapAccumulator:
             raise IndexError(f"slot {k} outside [0, {self.num_slots})")
         return self.buffer[:, k]
 
+    def accepts(self, shape, dtype) -> bool:
+        """True when a kernel can write a map of this shape / dtype straight into the next slot."""
+        return (self.cursor < self.num_slots and tuple(shape) == (self.batch,) + self.map_shape and dtype == self.buffer.dtype)
+
+    def fit(self, map_shape: Sequence[int]) -> None:
+        """Re-shape the (still empty) buffer for maps of another per-sample shape than the one it was built for
+        (flip_threshold returns [B,1,H,W] maps for [B,C,H,W] samples)."""
+        map_shape = tuple(int(s) for s in map_shape)
+        if map_shape == self.map_shape:
+            return
+        if self.cursor != 0:
+            raise ValueError(f"map of shape {map_shape} does not fit accumulator slots of shape {self.map_shape}")
+        self.map_shape = map_shape
+        self.buffer = torch.empty((self.batch, self.num_slots) + map_shape, device=self.buffer.device, dtype=self.buffer.dtype)
+
     def next_slot(self, shape=None, dtype=None) -> torch.Tensor:
         """The view the next in-window step writes its map into (advances the cursor)."""
         if self.cursor >= self.num_slots:
@@ -52,6 +67,8 @@ class UncertaintyMapAccumulator:
 
     def stash(self, tensor: torch.Tensor, k: Optional[int] = None) -> torch.Tensor:
         """Copy (and convert) a per-step tensor into slot k (default: next) with one du_accumulate_slot launch."""
+        if k is None:
+            self.fit(tensor.shape[1:])
         view = self.next_slot(tensor.shape) if k is None else self.slot(k)
         ops.accumulate_slot(tensor, view)
         return view

@@ -6,6 +6,8 @@
 
 namespace du {
 static thread_local char g_err[512] = "";
+static thread_local int g_want_device = -1;   // -1: whatever device is current (single-GPU processes never call du_set_device)
+int wanted_device() { return g_want_device; }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -29,7 +31,11 @@ extern "C" int du_num_sms(int device) {
   return n;
 }
 extern "C" int du_set_device(int device) {
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return du::check_cuda(e, "cudaSetDevice");
+  if (device < 0) { du::g_want_device = -1; return DU_OK; }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return du::check_cuda(e, "cudaGetDeviceCount");
+  if (device >= count) return du::set_error(DU_ERR_BAD_ARG, "du_set_device: device %d out of range (%d devices)", device, count);
+  du::g_want_device = device;
   return DU_OK;
 }

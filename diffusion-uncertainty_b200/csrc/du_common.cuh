@@ -19,6 +19,27 @@ int check_cuda(cudaError_t e, const char* what);
   } while (0)
 #define DU_LAUNCH_CHECK(name) DU_CUDA(cudaPeekAtLastError())
 
+// ---- device selection (du_abi.cu) -----------------------------------------------------------------
+// du_set_device() records the device the calling THREAD wants its next calls to run on; it does not touch the CUDA
+// current device.  Every launching entry point holds a DeviceGuard: if the thread's current device differs from the
+// wanted one it switches for the duration of the call and restores the caller's device on return, so the library never
+// changes what torch.cuda.current_device() reports and never launches on a stale device (the selection is thread-local
+// on both sides of the ABI).
+int wanted_device();
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  DeviceGuard() {
+    const int want = wanted_device();
+    if (want < 0) return;
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    if (prev != want && cudaSetDevice(want) == cudaSuccess) switched = true;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 inline bool dtype_ok(int dt) { return dt == DU_F32 || dt == DU_F16 || dt == DU_BF16; }
 inline int dtype_size(int dt) { return dt == DU_F32 ? 4 : 2; }
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -65,6 +86,20 @@ __device__ __forceinline__ uint4 ldg_stream_128_pol(const void* p, uint64_t pol)
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
       : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+
+// Plain (coherent) global loads for data another kernel may still have been writing while THIS kernel was already resident
+// (the batch-sum row S of a step launched as a programmatic dependent): the non-coherent path (__ldg / ld.global.nc) is
+// only defined for memory that is read-only for the kernel's whole lifetime.
+__device__ __forceinline__ float4 ld_coherent_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_coherent_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p));
   return r;
 }
 

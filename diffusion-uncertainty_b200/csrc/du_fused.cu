@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_step_kernel(const __grid_
   }
   if (__any_sync(0xffffffffu, nan_seen) && (tid & 31) == 0) misc[3] = 1u;
   if (use_tmem) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-  if (tid == 0) {  // phase C inputs -> L2 while the select runs
+  if (tid == 0 && !p.skip_ddim) {  // phase C inputs -> L2 while the select runs
     prefetch_l2_bulk(reinterpret_cast<const char*>(p.sample) + (b * p.sample_stride + base) * (p.sample_dtype == DU_F32 ? 4 : 2),
                      (uint32_t)(L * (p.sample_dtype == DU_F32 ? 4 : 2)));
     if (!use_tmem) prefetch_l2_bulk(reinterpret_cast<const char*>(p.eps) + erow * (int64_t)sizeof(T), (uint32_t)(L * sizeof(T)));
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_step_kernel(const __grid_
 
   // ---------------------------------------------------------------- phase C: mask + posterior + DDIM
   const bool fast_c = p.ddim.prediction_type == DU_PRED_EPSILON && !p.ddim.use_clipped_model_output &&
-                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32;
+                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32 && !p.skip_ddim;
   if constexpr (sizeof(T) == 4) {
     if (fast_c && use_tmem) guided_update_slice<T, THREADS, true, true>(kp, u_s, thr, b, base, tbase);
     else if (fast_c) guided_update_slice<T, THREADS, true, false>(kp, u_s, thr, b, base, 0u);
@@ -241,6 +241,7 @@ extern "C" int du_fused_supported(int64_t n, int score_dtype) {
 }
 
 extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!p) return set_error(DU_ERR_BAD_ARG, "du_fused_uncertainty_step: null params");
   if (p->M < 1 || p->M > DU_MAX_M) return set_error(DU_ERR_BAD_ARG, "du_fused_uncertainty_step: M=%d must be in [1,%d]", p->M, DU_MAX_M);
   if (!dtype_ok(p->score_dtype) || !dtype_ok(p->sample_dtype) || !dtype_ok(p->prev_dtype))
@@ -252,16 +253,18 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
   if (p->n > ((int64_t)1 << 24)) return set_error(DU_ERR_TOO_LARGE, "quantile() input tensor is too large");
   if (p->B == 0) return DU_OK;
   if (p->B > 65535) return set_error(DU_ERR_TOO_LARGE, "du_fused_uncertainty_step: batch > 65535, split the call");
-  if (!p->eps || !p->sample || !p->unc_out || !p->prev_out) return set_error(DU_ERR_BAD_ARG, "du_fused_uncertainty_step: null tensor");
+  if (!p->eps || !p->unc_out) return set_error(DU_ERR_BAD_ARG, "du_fused_uncertainty_step: null tensor");
+  if (p->skip_ddim ? !p->eps_out : (!p->sample || !p->prev_out))
+    return set_error(DU_ERR_BAD_ARG, p->skip_ddim ? "du_fused_uncertainty_step: skip_ddim needs eps_out" : "du_fused_uncertainty_step: null tensor");
   const int vec = p->score_dtype == DU_F32 ? 4 : 8;
   FusedPlan plan;
   if (!fused_plan(p->n, vec, p->B, &plan))
     return set_error(DU_ERR_TOO_LARGE, "du_fused_uncertainty_step: rows of %lld elements do not fit cluster shared memory; use the unfused calls", (long long)p->n);
   // 128-bit access requirements
   bool ok = aligned(p->eps, 16) && (p->eps_stride % vec == 0) && (p->score_stride % vec == 0) &&
-            aligned(p->sample, 16) && (p->sample_stride % (p->sample_dtype == DU_F32 ? 4 : 8) == 0) &&
+            (p->skip_ddim || (aligned(p->sample, 16) && (p->sample_stride % (p->sample_dtype == DU_F32 ? 4 : 8) == 0))) &&
             aligned(p->unc_out, 16) && (p->unc_stride % 4 == 0) &&
-            vec4_ok(p->prev_out, p->prev_stride, p->prev_dtype) && vec4_ok(p->x0_out, p->x0_stride, p->prev_dtype) &&
+            (p->skip_ddim || (vec4_ok(p->prev_out, p->prev_stride, p->prev_dtype) && vec4_ok(p->x0_out, p->x0_stride, p->prev_dtype))) &&
             vec4_ok(p->eps_out, p->eps_out_stride, DU_F32) && vec4_ok(p->mask_out, p->mask_out_stride, DU_F32) &&
             (!p->S || (aligned(p->S, 16) && (p->S_broadcast || p->S_stride % 4 == 0)));
   for (int m = 0; m < p->M; ++m) {
@@ -291,7 +294,7 @@ extern "C" int du_fused_uncertainty_step(const du_fused_params* p, du_stream_t s
     const char* e_tm = getenv("DU_FUSED_TMEM");
     const int64_t ng = kp.L / 4;
     const bool fast_c = p->ddim.prediction_type == DU_PRED_EPSILON && !p->ddim.use_clipped_model_output &&
-                        p->sample_dtype == DU_F32 && p->prev_dtype == DU_F32;
+                        p->sample_dtype == DU_F32 && p->prev_dtype == DU_F32 && !p->skip_ddim;
     if (!(e_tm && atoi(e_tm) == 0) && p->score_dtype == DU_F32 && p->moments_mode != DU_MOM_VAR_UNBIASED && fast_c && ng % 32 == 0) {
       const uint32_t trips = (uint32_t)((ng + plan.threads - 1) / plan.threads);
       const uint32_t need = trips * 4u * (uint32_t)(plan.threads / 128);

@@ -535,11 +535,14 @@ __device__ __forceinline__ void guided_update_slice(const FusedKParams& kp, cons
   const float* Srow = p.S ? (p.S + (p.S_broadcast ? 0 : b * p.S_stride) + base) : nullptr;
   const int pt = FAST ? DU_PRED_EPSILON : dc.prediction_type;
   const bool reclip = FAST ? false : (dc.use_clipped_model_output != 0);
+  const bool skip = FAST ? false : (p.skip_ddim != 0);   // guided score only (no sample, no x_{t-1}); generic instantiation
   int trip = 0;
 #pragma unroll 4
   for (int g = tid; g < ng4; g += THREADS, ++trip) {
     float s[4], e0[4], S[4];
-    if (FAST) {
+    if (skip) {
+      s[0] = s[1] = s[2] = s[3] = 0.0f;
+    } else if (FAST) {
       const uint4 r = ldg_stream_128_pol(reinterpret_cast<const float*>(p.sample) + xrow + 4 * g, kL2EvictFirst);
       s[0] = __uint_as_float(r.x); s[1] = __uint_as_float(r.y); s[2] = __uint_as_float(r.z); s[3] = __uint_as_float(r.w);
     } else {
@@ -552,7 +555,7 @@ __device__ __forceinline__ void guided_update_slice(const FusedKParams& kp, cons
       load4(p.eps, erow + 4 * g, FV::DT, e0);
     }
     if (Srow) {
-      const float4 s4 = __ldg(reinterpret_cast<const float4*>(Srow + 4 * g));
+      const float4 s4 = ld_coherent_f4(Srow + 4 * g);
       S[0] = s4.x; S[1] = s4.y; S[2] = s4.z; S[3] = s4.w;
     } else {
 #pragma unroll
@@ -578,8 +581,8 @@ __device__ __forceinline__ void guided_update_slice(const FusedKParams& kp, cons
       x0v[e] = x0;
     }
     if (FAST) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.prev_out) + b * p.prev_stride + base + 4 * g) = make_float4(pv[0], pv[1], pv[2], pv[3]);
-    else store4(p.prev_out, b * p.prev_stride + base + 4 * g, p.prev_dtype, pv);
-    if (p.x0_out) store4(p.x0_out, b * p.x0_stride + base + 4 * g, p.prev_dtype, x0v);
+    else if (!skip) store4(p.prev_out, b * p.prev_stride + base + 4 * g, p.prev_dtype, pv);
+    if (p.x0_out && !skip) store4(p.x0_out, b * p.x0_stride + base + 4 * g, p.prev_dtype, x0v);
     if (p.eps_out) store4(p.eps_out, b * p.eps_out_stride + base + 4 * g, DU_F32, eg);
     if (p.mask_out) store4(p.mask_out, b * p.mask_out_stride + base + 4 * g, DU_F32, mk);
   }

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
         for (int h = 0; h < VEC / 4; ++h) raw_s[h] = ldg_stream_128_pol(xs + g_elems + 4 * h, pol);
         if (Srow) {
 #pragma unroll
-          for (int h = 0; h < VEC / 4; ++h) raw_S[h] = __ldg(reinterpret_cast<const float4*>(Srow + g_elems + 4 * h));
+          for (int h = 0; h < VEC / 4; ++h) raw_S[h] = ld_coherent_f4(Srow + g_elems + 4 * h);
         }
       }
       if (from_scores) {
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
         const float mk = (higher ? (u > thr) : (u < thr)) ? 1.0f : 0.0f;
         float eg, x0, pv;
         const float e0 = cand_e[i];
-        const float Sv = Srow ? __ldg(Srow + o) : e0;   // the S row is shared by every image of the batch: L2 / L1 resident
+        const float Sv = Srow ? ld_coherent_f1(Srow + o) : e0;   // the S row is shared by every image of the batch: L2 / L1 resident
         guided_elem(dc, post_M, inv_ah, inv_sa, u, e0, cand_s[i], Sv, mk, eg, x0, pv);
         prow[o] = pv;
         if constexpr (OUTS) {
@@ -444,7 +444,7 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
   const char* e_p = getenv("DU_FUSED_PRED");
   if (e_p && atoi(e_p) == 0) return 0;
   const bool fast_c = p.ddim.prediction_type == DU_PRED_EPSILON && !p.ddim.use_clipped_model_output &&
-                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32;
+                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32 && !p.skip_ddim;
   if (!fast_c || (plan.threads != 512 && plan.threads != 1024)) return 0;
   // elements per thread and trip: 4, except 16-bit scores with a runtime-M instance (16-byte vectors of 8)
   const bool outs_req = p.x0_out || p.eps_out || p.mask_out;

@@ -180,6 +180,7 @@ extern "C" int du_moments(const void* const* scores, int M, int64_t score_stride
                           const void* center, int64_t center_stride, int center_dtype, int mode,
                           int64_t B, int64_t n, void* unc_out, int64_t unc_stride, int unc_dtype,
                           float* mean_out, int64_t mean_stride, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!scores || M < 1 || M > DU_MAX_M) return set_error(DU_ERR_BAD_ARG, "du_moments: M=%d must be in [1,%d]", M, DU_MAX_M);
   if (B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_moments: negative size");
   if (B == 0 || n == 0) return DU_OK;
@@ -222,6 +223,7 @@ extern "C" int du_moments(const void* const* scores, int M, int64_t score_stride
 
 extern "C" int du_moments_merge(const float* const* means, const float* const* m2s, const int* counts, int R,
                                 int mode, int64_t N, float* unc_out, float* mean_out, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (R < 1 || R > DU_MAX_M || !m2s || !counts || !unc_out || N < 0)
     return set_error(DU_ERR_BAD_ARG, "du_moments_merge: bad arguments (R=%d)", R);
   if (mode != DU_MOM_CENTERED && mode != DU_MOM_VAR_UNBIASED && mode != DU_MOM_STD_UNBIASED)

@@ -89,6 +89,7 @@ __global__ void rng_advance_kernel(uint64_t* state, uint64_t increment) {
 using namespace du;
 
 extern "C" int du_randn_offset_increment(int64_t N, uint64_t* increment_out) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (N < 0 || !increment_out) return set_error(DU_ERR_BAD_ARG, "du_randn_offset_increment: bad arguments");
   if (N == 0) { *increment_out = 0; return DU_OK; }
   RngGeometry g;
@@ -101,6 +102,7 @@ extern "C" int du_randn_offset_increment(int64_t N, uint64_t* increment_out) {
 extern "C" int du_perturb_randn(const void* x, int x_dtype, int64_t N, uint64_t seed, uint64_t offset,
                                 const uint64_t* device_state, float a, float b, void* out, int out_dtype,
                                 void* noise_out, int noise_dtype, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (N < 0 || !dtype_ok(noise_dtype) || (x && (!dtype_ok(x_dtype) || !out || !dtype_ok(out_dtype))) || (!x && !noise_out))
     return set_error(DU_ERR_BAD_ARG, "du_perturb_randn: bad arguments");
   if (N > 0x7fffffffLL)   // torch splits such tensors into 32-bit-indexable pieces with one generator call each
@@ -120,6 +122,7 @@ extern "C" int du_perturb_randn(const void* x, int x_dtype, int64_t N, uint64_t 
 }
 
 extern "C" int du_rng_advance(uint64_t* device_state, uint64_t increment, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!device_state) return set_error(DU_ERR_BAD_ARG, "du_rng_advance: null state");
   rng_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(device_state, increment);
   DU_LAUNCH_CHECK("rng_advance_kernel");

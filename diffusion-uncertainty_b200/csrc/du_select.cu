@@ -132,6 +132,7 @@ extern "C" size_t du_quantile_scratch_bytes(int64_t B, int64_t n) {
 extern "C" int du_quantile_threshold(const float* u, int64_t B, int64_t n, int64_t stride, float q, int lerp_fma,
                                      float* thr_out, int32_t* rank_out, float* val_out, void* scratch, size_t scratch_bytes,
                                      du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   (void)scratch; (void)scratch_bytes;
   if (B < 0) return set_error(DU_ERR_BAD_ARG, "du_quantile_threshold: negative batch");
   if (!(q >= 0.0f && q <= 1.0f)) return set_error(DU_ERR_BAD_ARG, "quantile() q values must be in the range [0, 1]");

@@ -116,6 +116,12 @@ __device__ __forceinline__ float guided_eps(int guidance, float eps, float m, fl
       return __fmul_rn(eps, m);
     case DU_GUIDE_LINCOMB:   // a*eps + lam*g (a travels in post_M): SU/scheduling_ddim_mc_dropout_gradient.py:514
       return __fadd_rn(__fmul_rn(post_M, eps), __fmul_rn(lam, aux));
+    case DU_GUIDE_MUL_BLEND:   // eps (1-m) + eps m g: generate_samples.py:953 (legacy percentile loop)
+      return __fadd_rn(__fmul_rn(eps, __fsub_rn(1.0f, m)), __fmul_rn(__fmul_rn(eps, m), aux));
+    case DU_GUIDE_SIGN_ADD: {   // eps + u * sign(n) * m: PU/..._guided_second_order.py:249 (torch.sign: -1 / 0 / +1, NaN -> NaN)
+      const float sg = (aux > 0.0f) ? 1.0f : ((aux < 0.0f) ? -1.0f : ((aux == 0.0f) ? 0.0f : aux));
+      return __fadd_rn(eps, __fmul_rn(__fmul_rn(u, sg), m));
+    }
     default:
       return eps;
   }
@@ -176,16 +182,47 @@ struct GuidedF {
 // ---- F7 perturbation, F8 slot copy ---------------------------------------------------------------------
 struct PerturbF {
   const void* x; int64_t x_stride; int x_dtype;
-  const void* nz; int64_t nz_stride; int nz_dtype;
+  const void* nz; int64_t nz_stride; int nz_dtype;   // null: out = a * x
   float a, b_;
+  const float* a_rows; const float* b_rows;          // per-row scalars (du_perturb_rows), else null
   void* out; int64_t out_stride; int out_dtype;
   template <int VEC> __device__ __forceinline__ void run(int64_t b, int64_t i) const {
     float xv[VEC], nv[VEC], o[VEC];
     loadv<VEC>(x, b * x_stride + i, x_dtype, xv);
-    loadv<VEC>(nz, b * nz_stride + i, nz_dtype, nv);
+    const float aa = a_rows ? __ldg(a_rows + b) : a, bb = b_rows ? __ldg(b_rows + b) : b_;
+    if (nz) {
+      loadv<VEC>(nz, b * nz_stride + i, nz_dtype, nv);
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) o[e] = __fadd_rn(__fmul_rn(a, xv[e]), __fmul_rn(b_, nv[e]));
+      for (int e = 0; e < VEC; ++e) o[e] = __fadd_rn(__fmul_rn(aa, xv[e]), __fmul_rn(bb, nv[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) o[e] = __fmul_rn(aa, xv[e]);
+    }
     storev<VEC>(out, b * out_stride + i, out_dtype, o);
+  }
+};
+
+// ---- EMA of the map with bias correction and square root (PU/..._guided_second_order.py:212-218) ------------------------
+struct EmaF {
+  const float* mom; const void* u; int u_dtype; float beta, one_minus_beta, denom;
+  float* mom_out; float* corrected; float* root;
+  template <int VEC> __device__ __forceinline__ void run(int64_t b, int64_t i) const {
+    float uv[VEC], mv[VEC], cv[VEC], rv[VEC];
+    loadv<VEC>(u, i, u_dtype, uv);
+    if (mom) {
+      loadv<VEC>(mom, i, DU_F32, mv);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) mv[e] = __fadd_rn(__fmul_rn(beta, mv[e]), __fmul_rn(one_minus_beta, uv[e]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) mv[e] = uv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) { cv[e] = __fdiv_rn(mv[e], denom); rv[e] = __fsqrt_rn(cv[e]); }
+    storev<VEC>(mom_out, i, DU_F32, mv);
+    if (corrected) storev<VEC>(corrected, i, DU_F32, cv);
+    if (root) storev<VEC>(root, i, DU_F32, rv);
+    (void)b;
   }
 };
 
@@ -368,6 +405,7 @@ using namespace du;
 
 extern "C" int du_threshold_mask(const void* u, int64_t u_stride, int u_dtype, const float* thr, int higher,
                                  int64_t B, int64_t n, float* mask_out, int64_t mask_stride, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(u, u_dtype) || !thr || !mask_out || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_threshold_mask: bad arguments");
   ThrMaskF f{u, u_stride, u_dtype, thr, nullptr, DU_F32, higher, mask_out, mask_stride};
   bool vec = (n % 4 == 0) && vec4_ok(u, u_stride, u_dtype) && vec4_ok(mask_out, mask_stride, DU_F32);
@@ -377,6 +415,7 @@ extern "C" int du_threshold_mask(const void* u, int64_t u_stride, int u_dtype, c
 extern "C" int du_tensor_threshold_mask(const void* u, int64_t u_stride, int u_dtype, const void* thr_map, int thr_dtype,
                                         int higher, int64_t B, int64_t n, float* mask_out, int64_t mask_stride,
                                         du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(u, u_dtype) || !check_view(thr_map, thr_dtype) || !mask_out || B < 0 || n < 0)
     return set_error(DU_ERR_BAD_ARG, "du_tensor_threshold_mask: bad arguments");
   ThrMaskF f{u, u_stride, u_dtype, nullptr, thr_map, thr_dtype, higher, mask_out, mask_stride};
@@ -395,6 +434,7 @@ extern "C" size_t du_znorm_scratch_bytes(int64_t B, int64_t n) { return (size_t)
 
 extern "C" int du_znorm_stats(const void* u, int64_t u_stride, int u_dtype, int64_t B, int64_t n, float* stats_out,
                               void* scratch, size_t scratch_bytes, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(u, u_dtype) || !stats_out || !scratch || B <= 0 || n <= 0) return set_error(DU_ERR_BAD_ARG, "du_znorm_stats: bad arguments");
   if (scratch_bytes < du_znorm_scratch_bytes(B, n) || !aligned(scratch, 8)) return set_error(DU_ERR_SCRATCH, "du_znorm_stats: scratch too small or misaligned");
   int blocks = znorm_blocks(B * n);
@@ -407,6 +447,7 @@ extern "C" int du_znorm_stats(const void* u, int64_t u_stride, int u_dtype, int6
 }
 
 extern "C" int du_znorm_stats_combine(const float* stats_in, int R, float* stats_out, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!stats_in || !stats_out || R < 1) return set_error(DU_ERR_BAD_ARG, "du_znorm_stats_combine: bad arguments");
   znorm_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_in, R, stats_out);
   DU_LAUNCH_CHECK("znorm_combine_kernel");
@@ -416,6 +457,7 @@ extern "C" int du_znorm_stats_combine(const float* stats_in, int R, float* stats
 extern "C" int du_znorm_weights(const void* u, int64_t u_stride, int u_dtype, const float* stats, int normalize, int mode,
                                 float thr, int64_t B, int64_t n, float* z_out, int64_t z_stride, float* w_out,
                                 int64_t w_stride, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(u, u_dtype) || (normalize && !stats) || (!z_out && !w_out) || B < 0 || n < 0)
     return set_error(DU_ERR_BAD_ARG, "du_znorm_weights: bad arguments");
   if (mode < DU_ZN_BELOW || mode > DU_ZN_MULTISCALE) return set_error(DU_ERR_BAD_ARG, "du_znorm_weights: bad mode %d", mode);
@@ -436,6 +478,7 @@ extern "C" int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_
                             int64_t B, int64_t n, void* prev_out, int64_t prev_stride, int prev_dtype, void* x0_out,
                             int64_t x0_stride, int x0_dtype, void* eps_out, int64_t eps_stride, int eps_dtype,
                             du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   int rc = check_coeffs(c, "du_ddim_step");
   if (rc) return rc;
   if (!check_view(model_output, mo_dtype) || !check_view(sample, s_dtype) || B < 0 || n < 0)
@@ -453,8 +496,9 @@ extern "C" int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_
 }
 
 extern "C" int du_guided_step(const du_guided_params* p, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!p) return set_error(DU_ERR_BAD_ARG, "du_guided_step: null params");
-  if (p->guidance < DU_GUIDE_NONE || p->guidance > DU_GUIDE_LINCOMB) return set_error(DU_ERR_BAD_ARG, "du_guided_step: bad guidance %d", p->guidance);
+  if (p->guidance < DU_GUIDE_NONE || p->guidance > DU_GUIDE_MUL_BLEND) return set_error(DU_ERR_BAD_ARG, "du_guided_step: bad guidance %d", p->guidance);
   if (!check_view(p->eps, p->eps_dtype) || p->B < 0 || p->n < 0) return set_error(DU_ERR_BAD_ARG, "du_guided_step: bad eps view");
   if (!p->skip_ddim) {
     int rc = check_coeffs(&p->ddim, "du_guided_step");
@@ -467,8 +511,9 @@ extern "C" int du_guided_step(const du_guided_params* p, du_stream_t stream) {
     return set_error(DU_ERR_BAD_ARG, "du_guided_step: guidance needs thr or mask");
   if (p->mask_period < 0 || (p->mask_period > 0 && (!p->mask || p->n % p->mask_period != 0)))
     return set_error(DU_ERR_BAD_ARG, "du_guided_step: mask_period must divide the row length");
-  if ((p->thr || p->guidance == DU_GUIDE_POSTERIOR) && !p->u) return set_error(DU_ERR_BAD_ARG, "du_guided_step: u required");
-  if ((p->guidance == DU_GUIDE_GRAD_BLEND || p->guidance == DU_GUIDE_GRAD_ADD || p->guidance == DU_GUIDE_LINCOMB) && !check_view(p->aux, p->aux_dtype))
+  if ((p->thr || p->guidance == DU_GUIDE_POSTERIOR || p->guidance == DU_GUIDE_SIGN_ADD) && !p->u) return set_error(DU_ERR_BAD_ARG, "du_guided_step: u required");
+  if ((p->guidance == DU_GUIDE_GRAD_BLEND || p->guidance == DU_GUIDE_GRAD_ADD || p->guidance == DU_GUIDE_LINCOMB || p->guidance == DU_GUIDE_SIGN_ADD ||
+       p->guidance == DU_GUIDE_MUL_BLEND) && !check_view(p->aux, p->aux_dtype))
     return set_error(DU_ERR_BAD_ARG, "du_guided_step: gradient tensor required");
   if (p->aux && !dtype_ok(p->aux_dtype)) return set_error(DU_ERR_DTYPE, "du_guided_step: bad aux dtype");
   if (!p->prev_out && !p->x0_out && !p->eps_out && !p->mask_out) return set_error(DU_ERR_BAD_ARG, "du_guided_step: no output requested");
@@ -484,6 +529,7 @@ extern "C" int du_guided_step(const du_guided_params* p, du_stream_t stream) {
 }
 
 extern "C" int du_batch_sum(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, float* out, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(x, x_dtype) || !out || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_batch_sum: bad arguments");
   if (n == 0) return DU_OK;
   const int vec = (x_dtype == DU_F32) ? 4 : 8;
@@ -508,15 +554,38 @@ extern "C" int du_batch_sum(const void* x, int64_t x_stride, int x_dtype, int64_
 extern "C" int du_perturb(const void* x, int64_t x_stride, int x_dtype, const void* noise, int64_t noise_stride, int noise_dtype,
                           float a, float b, int64_t B, int64_t n, void* out, int64_t out_stride, int out_dtype,
                           du_stream_t stream) {
-  if (!check_view(x, x_dtype) || !check_view(noise, noise_dtype) || !check_view(out, out_dtype) || B < 0 || n < 0)
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
+  if (!check_view(x, x_dtype) || (noise && !check_view(noise, noise_dtype)) || !check_view(out, out_dtype) || B < 0 || n < 0)
     return set_error(DU_ERR_BAD_ARG, "du_perturb: bad arguments");
-  PerturbF f{x, x_stride, x_dtype, noise, noise_stride, noise_dtype, a, b, out, out_stride, out_dtype};
+  PerturbF f{x, x_stride, x_dtype, noise, noise_stride, noise_dtype, a, b, nullptr, nullptr, out, out_stride, out_dtype};
   bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && vec4_ok(noise, noise_stride, noise_dtype) && vec4_ok(out, out_stride, out_dtype);
   return launch_rows(B, n, vec, f, (cudaStream_t)stream);
 }
 
+extern "C" int du_perturb_rows(const void* x, int64_t x_stride, int x_dtype, const void* noise, int64_t noise_stride, int noise_dtype,
+                               const float* a_rows, const float* b_rows, int64_t B, int64_t n, void* out, int64_t out_stride,
+                               int out_dtype, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
+  if (!check_view(x, x_dtype) || !check_view(noise, noise_dtype) || !check_view(out, out_dtype) || !a_rows || !b_rows || B < 0 || n < 0)
+    return set_error(DU_ERR_BAD_ARG, "du_perturb_rows: bad arguments");
+  PerturbF f{x, x_stride, x_dtype, noise, noise_stride, noise_dtype, 0.0f, 0.0f, a_rows, b_rows, out, out_stride, out_dtype};
+  bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && vec4_ok(noise, noise_stride, noise_dtype) && vec4_ok(out, out_stride, out_dtype);
+  return launch_rows(B, n, vec, f, (cudaStream_t)stream);
+}
+
+extern "C" int du_ema_update(const float* momentum, const void* u, int u_dtype, float beta, float one_minus_beta, float denom, int64_t N,
+                             float* momentum_out, float* corrected_out, float* sqrt_out, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
+  if (!check_view(u, u_dtype) || !momentum_out || N < 0) return set_error(DU_ERR_BAD_ARG, "du_ema_update: bad arguments");
+  EmaF f{momentum, u, u_dtype, beta, one_minus_beta, denom, momentum_out, corrected_out, sqrt_out};
+  bool vec = (N % 4 == 0) && vec4_ok(u, 0, u_dtype) && vec4_ok(momentum, 0, DU_F32) && vec4_ok(momentum_out, 0, DU_F32) &&
+             vec4_ok(corrected_out, 0, DU_F32) && vec4_ok(sqrt_out, 0, DU_F32);
+  return launch_rows(1, N, vec, f, (cudaStream_t)stream);
+}
+
 extern "C" int du_image_uint8(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, uint8_t* out,
                               int64_t out_stride, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(x, x_dtype) || !out || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_image_uint8: bad arguments");
   ImageU8F f{x, x_stride, x_dtype, out, out_stride};
   bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && aligned(out, 4) && (out_stride % 4 == 0);
@@ -525,6 +594,7 @@ extern "C" int du_image_uint8(const void* x, int64_t x_stride, int x_dtype, int6
 
 extern "C" int du_accumulate_slot(const void* src, int64_t src_stride, int src_dtype, int64_t B, int64_t n, void* dst,
                                   int64_t dst_stride, int dst_dtype, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(src, src_dtype) || !check_view(dst, dst_dtype) || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_accumulate_slot: bad arguments");
   CopyF f{src, src_stride, src_dtype, dst, dst_stride, dst_dtype};
   bool vec = (n % 4 == 0) && vec4_ok(src, src_stride, src_dtype) && vec4_ok(dst, dst_stride, dst_dtype);

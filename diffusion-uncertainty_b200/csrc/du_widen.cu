@@ -88,7 +88,7 @@ struct MomentsBwdF {
   template <int VEC> __device__ __forceinline__ void run(int64_t b, int64_t i) const {
     float g[VEC], c[VEC], sum[VEC];
     loadv<VEC>(gu, b * gu_stride + i, gu_dtype, g);
-    const bool has_c = (mode != DU_MOM_VAR_UNBIASED);
+    const bool has_c = (mode != DU_MOM_VAR_UNBIASED && mode != DU_MOM_STD_UNBIASED);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) { c[k] = 0.0f; sum[k] = 0.0f; }
     if (has_c) loadv<VEC>(center, b * center_stride + i, center_dtype, c);
@@ -99,10 +99,25 @@ struct MomentsBwdF {
       for (int k = 0; k < VEC; ++k) sum[k] += s[k];
     }
     float ref[VEC], coef;   // du/ds_m = coef * (s_m - ref)
-    if (mode == DU_MOM_VAR_UNBIASED) {
+    float cstd[VEC];        // STD_UNBIASED: per-element factor 1 / ((M-1) std)
+    if (mode == DU_MOM_VAR_UNBIASED || mode == DU_MOM_STD_UNBIASED) {
       coef = 2.0f / (float)(M - 1);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) ref[k] = sum[k] / (float)M;
+      if (mode == DU_MOM_STD_UNBIASED) {   // d std / d s_m = (s_m - mean) / ((M-1) std)   (generate_samples.py:941-943)
+        float ss[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) ss[k] = 0.0f;
+        for (int m = 0; m < M; ++m) {
+          float s[VEC];
+          loadv<VEC>(scores[m], b * score_stride + i, score_dtype, s);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) { const float d = s[k] - ref[k]; ss[k] = fmaf(d, d, ss[k]); }
+        }
+        coef = 1.0f;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) cstd[k] = 1.0f / ((float)(M - 1) * sqrtf(ss[k] / (float)(M - 1)));
+      }
     } else if (mode == DU_MOM_CENTERED) {
       coef = 2.0f / (float)M;
 #pragma unroll
@@ -116,7 +131,7 @@ struct MomentsBwdF {
       float s[VEC], o[VEC];
       loadv<VEC>(scores[m], b * score_stride + i, score_dtype, s);
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) o[k] = g[k] * (coef * (s[k] - ref[k]));
+      for (int k = 0; k < VEC; ++k) o[k] = g[k] * ((mode == DU_MOM_STD_UNBIASED ? cstd[k] : coef) * (s[k] - ref[k]));
       if (grads[m]) storev<VEC>(grads[m], b * grad_stride + i, grad_dtype, o);
     }
     if (grad_center && has_c) {
@@ -237,6 +252,7 @@ using namespace du;
 
 extern "C" int du_flip_h(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t C, int64_t H, int64_t W,
                          void* out, int64_t out_stride, int out_dtype, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!view_ok(x, x_dtype) || !view_ok(out, out_dtype) || B < 0 || C < 0 || H < 0 || W < 0) return set_error(DU_ERR_BAD_ARG, "du_flip_h: bad arguments");
   FlipF f{x, x_stride, x_dtype, H, W, out, out_stride, out_dtype};
   const int64_t n = C * H * W;
@@ -247,6 +263,7 @@ extern "C" int du_flip_h(const void* x, int64_t x_stride, int x_dtype, int64_t B
 extern "C" int du_flip_sqdiff(const void* eps, int64_t eps_stride, int eps_dtype, const void* flipped, int64_t f_stride, int f_dtype,
                               int64_t B, int64_t C, int64_t H, int64_t W, int channel_amax, float* out, int64_t out_stride,
                               du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!view_ok(eps, eps_dtype) || !view_ok(flipped, f_dtype) || !out || B < 0 || C < 0 || H < 0 || W < 0)
     return set_error(DU_ERR_BAD_ARG, "du_flip_sqdiff: bad arguments");
   const bool vec = (W % 4 == 0) && vec4_ok(eps, eps_stride, eps_dtype) && vec4_ok(flipped, f_stride, f_dtype) && vec4_ok(out, out_stride, DU_F32);
@@ -262,14 +279,16 @@ extern "C" int du_moments_backward(const void* const* scores, int M, int64_t sco
                                    int64_t center_stride, int center_dtype, int mode, const void* grad_u, int64_t gu_stride,
                                    int gu_dtype, int64_t B, int64_t n, void* const* grad_scores, int64_t grad_stride,
                                    int grad_dtype, void* grad_center, int64_t gc_stride, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!scores || !grad_scores || M < 1 || M > DU_MAX_M) return set_error(DU_ERR_BAD_ARG, "du_moments_backward: M must be in [1,%d]", DU_MAX_M);
-  if (mode != DU_MOM_VAR_UNBIASED && mode != DU_MOM_CENTERED && mode != DU_MOM_VAR_WITH_CENTER)
+  if (mode != DU_MOM_VAR_UNBIASED && mode != DU_MOM_CENTERED && mode != DU_MOM_VAR_WITH_CENTER && mode != DU_MOM_STD_UNBIASED)
     return set_error(DU_ERR_BAD_ARG, "du_moments_backward: mode %d has no backward", mode);
+  const bool no_centre = (mode == DU_MOM_VAR_UNBIASED || mode == DU_MOM_STD_UNBIASED);
   if (!dtype_ok(score_dtype) || !dtype_ok(grad_dtype) || !view_ok(grad_u, gu_dtype)) return set_error(DU_ERR_DTYPE, "du_moments_backward: bad dtype / null grad_u");
-  if (mode != DU_MOM_VAR_UNBIASED && !view_ok(center, center_dtype)) return set_error(DU_ERR_BAD_ARG, "du_moments_backward: mode needs a centre");
+  if (!no_centre && !view_ok(center, center_dtype)) return set_error(DU_ERR_BAD_ARG, "du_moments_backward: mode needs a centre");
   if (B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_moments_backward: bad sizes");
   MomentsBwdF f{};
-  bool vec = (n % 4 == 0) && vec4_ok(grad_u, gu_stride, gu_dtype) && (mode == DU_MOM_VAR_UNBIASED || vec4_ok(center, center_stride, center_dtype)) &&
+  bool vec = (n % 4 == 0) && vec4_ok(grad_u, gu_stride, gu_dtype) && (no_centre || vec4_ok(center, center_stride, center_dtype)) &&
              vec4_ok(grad_center, gc_stride, grad_dtype);
   for (int m = 0; m < M; ++m) {
     if (!scores[m]) return set_error(DU_ERR_BAD_ARG, "du_moments_backward: scores[%d] is null", m);
@@ -286,6 +305,7 @@ extern "C" int du_moments_backward(const void* const* scores, int M, int64_t sco
 }
 
 extern "C" int du_column_kth(const void* x, int dtype, int64_t N, int64_t n, int64_t row_stride, int64_t k, void* out, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!x || !out || N < 1 || n < 0 || k < 0 || k >= N) return set_error(DU_ERR_BAD_ARG, "du_column_kth: need N >= 1 rows and 0 <= k < N");
   if (n == 0) return DU_OK;
   const unsigned grid = (unsigned)((n + 255) / 256);
@@ -299,6 +319,7 @@ extern "C" int du_column_kth(const void* x, int dtype, int64_t N, int64_t n, int
 }
 
 extern "C" int du_row_sum(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_t n, float* out, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!view_ok(x, x_dtype) || !out || B < 0 || n < 0) return set_error(DU_ERR_BAD_ARG, "du_row_sum: bad arguments");
   if (B == 0) return DU_OK;
   const bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype);
@@ -309,6 +330,7 @@ extern "C" int du_row_sum(const void* x, int64_t x_stride, int x_dtype, int64_t 
 
 extern "C" int du_slot_sum(const void* x, int64_t x_stride, int64_t slot_stride, int x_dtype, int64_t B, int T, int64_t n,
                            float* out, int64_t out_stride, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!view_ok(x, x_dtype) || !out || B < 0 || n < 0 || T < 0) return set_error(DU_ERR_BAD_ARG, "du_slot_sum: bad arguments");
   SlotSumF f{x, x_stride, slot_stride, x_dtype, T, out, out_stride};
   const bool vec = (n % 4 == 0) && vec4_ok(x, x_stride, x_dtype) && (slot_stride % 4 == 0) && vec4_ok(out, out_stride, DU_F32);
@@ -318,6 +340,7 @@ extern "C" int du_slot_sum(const void* x, int64_t x_stride, int64_t slot_stride,
 extern "C" int du_dpm_solver_update(const void* sample, int64_t s_stride, int s_dtype, const void* m0, int64_t m0_stride, int m0_dtype,
                                     const void* m1, int64_t m1_stride, int m1_dtype, float a, float b, float c, float k,
                                     int64_t B, int64_t n, void* out, int64_t out_stride, int out_dtype, du_stream_t stream) {
+  du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!view_ok(sample, s_dtype) || !view_ok(m0, m0_dtype) || (m1 && !dtype_ok(m1_dtype)) || !view_ok(out, out_dtype) || B < 0 || n < 0)
     return set_error(DU_ERR_BAD_ARG, "du_dpm_solver_update: bad arguments");
   DpmUpdateF f{sample, s_stride, s_dtype, m0, m0_stride, m0_dtype, m1, m1_stride, m1_dtype, a, b, c, k, out, out_stride, out_dtype};

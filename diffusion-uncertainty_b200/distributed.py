@@ -85,7 +85,7 @@ class ShardedMoments:
         return ops.moments_merge(means, m2s, counts, mode=mode)
 
     def reduce(self, local_scores: Sequence[torch.Tensor], center: Optional[torch.Tensor], mode: str,
-               total_M: Optional[int] = None) -> torch.Tensor:
+               total_M: Optional[int] = None, empty_like: Optional[torch.Tensor] = None) -> torch.Tensor:
         """mode: 'var' (F1b), 'var_with_center' (F1c: the centre counts as one more sample, contributed by rank 0 only)
         or 'centered' (F1a: sum of squared deviations about the common centre / total M).
         total_M: the number of samples over all ranks when they were dealt out with `shard_samples` — the per-rank counts
@@ -94,7 +94,27 @@ class ShardedMoments:
         if mode not in ("var", "var_with_center", "centered"):
             raise ValueError(f"ShardedMoments: unsupported mode {mode!r}")
         n_local = len(local_scores)
-        if mode == "centered":
+        # everything that can raise is checked BEFORE the collective: a rank that raised after its peers had entered the
+        # all-gather would leave them waiting forever
+        counts = None
+        if total_M is not None:
+            counts = [shard_samples(total_M, r, self.world) + (1 if (mode == "var_with_center" and r == 0) else 0)
+                      for r in range(self.world)]
+            if shard_samples(total_M, self.rank, self.world) != n_local:
+                raise ValueError(f"ShardedMoments: rank {self.rank} holds {n_local} samples, shard_samples({total_M}) says "
+                                 f"{shard_samples(total_M, self.rank, self.world)}")
+        if n_local == 0:
+            # a rank without samples (M < world): a zero partial with count 0 is the identity of the Chan merge.  With
+            # 'var_with_center' rank 0 still contributes the centre as its one sample (mean = centre, M2 = 0).
+            like = center if center is not None else empty_like
+            if like is None:
+                raise ValueError("ShardedMoments: a rank without samples needs `center` or `empty_like` for the shape")
+            m2 = torch.zeros(like.shape, device=like.device, dtype=torch.float32)
+            if mode == "var_with_center" and self.rank == 0:
+                mean, count = center.to(torch.float32), 1
+            else:
+                mean, count = torch.zeros_like(m2), 0
+        elif mode == "centered":
             m2, mean = self._partial(local_scores, center, False)          # about the centre; mean unused
             count = n_local
         elif mode == "var_with_center" and self.rank == 0:
@@ -108,13 +128,7 @@ class ShardedMoments:
         packed = torch.stack([mean.float(), m2.float()], dim=0).contiguous()          # [2, ...]
         gathered = torch.empty((self.world,) + tuple(packed.shape), device=packed.device, dtype=packed.dtype)
         dist.all_gather_into_tensor(gathered.view(self.world * packed.shape[0], *packed.shape[1:]), packed, group=self.group)
-        if total_M is not None:
-            counts = [shard_samples(total_M, r, self.world) + (1 if (mode == "var_with_center" and r == 0) else 0)
-                      for r in range(self.world)]
-            if counts[self.rank] != count:
-                raise ValueError(f"ShardedMoments: rank {self.rank} holds {n_local} samples, shard_samples({total_M}) says "
-                                 f"{shard_samples(total_M, self.rank, self.world)}")
-        else:
+        if counts is None:
             counts_t = torch.tensor([count], device=packed.device, dtype=torch.int64)
             all_counts = torch.empty(self.world, device=packed.device, dtype=torch.int64)
             dist.all_gather_into_tensor(all_counts, counts_t, group=self.group)

@@ -167,8 +167,8 @@ def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, 
                 if save_intermediates:
                     inter.append(output.prev_sample)
                 if with_unc and scheduler.timestep_after_step >= t >= scheduler.timestep_end_step:
-                    if getattr(scheduler, "map_sink", None) is None:     # a scheduler that cannot write into the sink itself
-                        acc_u.stash(output.uncertainty)
+                    if not getattr(scheduler, "map_in_sink", False):     # the step did not write its map into the sink itself
+                        acc_u.stash(output.uncertainty)                  # (other dtype / shape than the slots: converted here)
                     acc_s.stash(output.pred_epsilon)
                 x = output.prev_sample
         finally:
@@ -204,3 +204,8 @@ def _sampling_loop(X_T, y, batch_size, device, model, scheduler, fid_evaluator, 
         results["uncertainty"] = host_unc
         results["score"] = host_score
     return results
+
+
+# the threshold-guided loops of the same reference module (generate_samples.py:721-983) live in guided_loops.py
+from .guided_loops import (generate_samples_model_scheduler_class_conditioned_with_percentile,  # noqa: E402,F401
+                           generate_samples_uvit_scheduler_class_conditioned_with_threshold)

@@ -6,6 +6,7 @@ All functions require CUDA tensors — there is no CPU fallback (BASELINE.json n
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -17,12 +18,14 @@ _MODES = {"var": L.MOM_VAR_UNBIASED, "centered": L.MOM_CENTERED, "var_with_cente
           "raw": L.MOM_RAW, "std": L.MOM_STD_UNBIASED, "partial": L.MOM_PARTIAL_M2}
 _PRED = {"epsilon": L.PRED_EPSILON, "sample": L.PRED_SAMPLE, "v_prediction": L.PRED_V}
 _GUIDE = {"none": L.GUIDE_NONE, "posterior": L.GUIDE_POSTERIOR, "grad_blend": L.GUIDE_GRAD_BLEND,
-          "grad_add": L.GUIDE_GRAD_ADD, "weights": L.GUIDE_WEIGHTS, "lincomb": L.GUIDE_LINCOMB}
+          "grad_add": L.GUIDE_GRAD_ADD, "weights": L.GUIDE_WEIGHTS, "lincomb": L.GUIDE_LINCOMB, "sign_add": L.GUIDE_SIGN_ADD,
+          "mul_blend": L.GUIDE_MUL_BLEND}
 _ZN = {"max": L.ZN_BELOW, "min": L.ZN_ABOVE, "below": L.ZN_BELOW, "above": L.ZN_ABOVE, "multiscale": L.ZN_MULTISCALE}
 
 # launches issued through this module since import (bench.py reports it as gpu_launches)
 launch_count = 0
-_current_device = [None]
+last_step_path = ""        # "fused" / "unfused": which implementation the last uncertainty_step() call took
+_tls = threading.local()   # device index last handed to du_set_device by THIS thread (the library keeps it thread-local too)
 
 
 def _count(n=1):
@@ -40,10 +43,14 @@ def _require_cuda(t: torch.Tensor, name: str):
 
 
 def _stream(t: torch.Tensor):
+    """Stream of t's device for the launch that follows, and tell the library which device that launch belongs to.  The
+    library switches to it only for the duration of the call (csrc/du_common.cuh DeviceGuard), so the caller's
+    torch.cuda.current_device() never changes and a later torch.cuda.set_device / another thread cannot make this stale:
+    the cached index mirrors the library's own thread-local value, which only this function writes."""
     idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
-    if _current_device[0] != idx:
+    if getattr(_tls, "device", None) != idx:
         L.check(L.load().du_set_device(idx))
-        _current_device[0] = idx
+        _tls.device = idx
     return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
@@ -182,8 +189,37 @@ class _MomentsFn(torch.autograd.Function):
 
 
 def moments_autograd(scores: Sequence[torch.Tensor], mode: str = "var", center: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Differentiable F1 reduction ('var' | 'centered' | 'var_with_center'), fp32 map."""
+    """Differentiable F1 reduction ('var' | 'std' | 'centered' | 'var_with_center'), fp32 map."""
     return _MomentsFn.apply(mode, center, *scores)
+
+
+class _X0Fn(torch.autograd.Function):
+    """x0 = (x - sb * eps) / sa, differentiable in eps: forward du_ddim_step (the reference's three rounded operations),
+    backward -(sb / sa) * g in one launch.  The threshold-guided loops keep this on the autograd graph because the gradient with
+    respect to eps flows through the re-noised model inputs (generate_samples.py:806, PU/uncertainty_guidance.py:89)."""
+
+    @staticmethod
+    def forward(ctx, eps, x, sa, sb):
+        ctx.k = -float(sb) / float(sa)
+        c = make_coeffs(float(sa), float(sb), 0.0, 0.0, clip_sample=False)
+        return ddim_step(eps.detach(), x.detach(), c, want_prev=False, want_x0=True)[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (scale(g.contiguous(), ctx.k) if ctx.needs_input_grad[0] else None), None, None, None
+
+
+def x0_autograd(eps: torch.Tensor, x: torch.Tensor, sa: float, sb: float) -> torch.Tensor:
+    return _X0Fn.apply(eps, x, sa, sb)
+
+
+def mask_greater(u: torch.Tensor, thr: torch.Tensor, higher: bool = True) -> torch.Tensor:
+    """(u > thr).float() with one threshold PER ELEMENT (thr has u's shape) — du_tensor_threshold_mask over the flattened tensors."""
+    if tuple(u.shape) != tuple(thr.shape):
+        raise ValueError("mask_greater: u and thr must have the same shape")
+    u = u if u.is_contiguous() else u.contiguous()
+    thr = thr if thr.is_contiguous() else thr.contiguous()
+    return tensor_threshold_mask(u.reshape(1, -1), thr.reshape(-1), higher=higher).reshape(u.shape)
 
 
 # ------------------------------------------------------------------------------------------------ N4 flips
@@ -513,16 +549,107 @@ def batch_sum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
 
 
 # ------------------------------------------------------------------------------------------------ F7 / F8
-def perturb(x: torch.Tensor, noise: torch.Tensor, a: float, b: float, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """a*x + b*noise (du_perturb)."""
-    xr, nr = Rows(x, "x"), Rows(noise, "noise")
-    _same_rows(xr, nr, "perturb")
-    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or torch.promote_types(x.dtype, noise.dtype))
-    rc = L.load().du_perturb(xr.ptr, xr.stride, xr.dt, nr.ptr, nr.stride, nr.dt, float(a), float(b), xr.B, xr.n,
-                             C.c_void_p(out.data_ptr()), xr.n, _DT[out.dtype], _stream(x))
+def perturb(x: torch.Tensor, noise: Optional[torch.Tensor], a: float, b: float = 0.0,
+            out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """a*x + b*noise (du_perturb); noise None: a*x."""
+    xr = Rows(x, "x")
+    nr = None
+    if noise is not None:
+        nr = Rows(noise, "noise")
+        _same_rows(xr, nr, "perturb")
+    out = torch.empty(x.shape, device=x.device,
+                      dtype=out_dtype or (x.dtype if noise is None else torch.promote_types(x.dtype, noise.dtype)))
+    if out.numel() == 0:
+        return out
+    rc = L.load().du_perturb(xr.ptr, xr.stride, xr.dt, nr.ptr if nr else NULL, nr.stride if nr else 0, nr.dt if nr else 0,
+                             float(a), float(b), xr.B, xr.n, C.c_void_p(out.data_ptr()), xr.n, _DT[out.dtype], _stream(x))
     L.check(rc)
     _count()
     return out
+
+
+def scale(x: torch.Tensor, a: float) -> torch.Tensor:
+    """a*x in one launch (du_perturb without a noise tensor)."""
+    return perturb(x, None, a)
+
+
+def perturb_rows(x: torch.Tensor, noise: torch.Tensor, a_rows: torch.Tensor, b_rows: torch.Tensor) -> torch.Tensor:
+    """a[b]*x[b] + b[b]*noise[b] with one scalar pair per row, read from device vectors (du_perturb_rows): add_noise /
+    get_velocity with a vector of per-sample timesteps."""
+    xr, nr = Rows(x, "x"), Rows(noise, "noise")
+    _same_rows(xr, nr, "perturb_rows")
+    _require_cuda(a_rows, "a_rows"); _require_cuda(b_rows, "b_rows")
+    a_rows = a_rows.reshape(-1).to(torch.float32).contiguous()
+    b_rows = b_rows.reshape(-1).to(torch.float32).contiguous()
+    if a_rows.numel() != xr.B or b_rows.numel() != xr.B:
+        raise ValueError("perturb_rows: one (a, b) pair per row expected")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.promote_types(x.dtype, noise.dtype))
+    if out.numel() == 0:
+        return out
+    L.check(L.load().du_perturb_rows(xr.ptr, xr.stride, xr.dt, nr.ptr, nr.stride, nr.dt, C.c_void_p(a_rows.data_ptr()),
+                                     C.c_void_p(b_rows.data_ptr()), xr.B, xr.n, C.c_void_p(out.data_ptr()), xr.n, _DT[out.dtype],
+                                     _stream(x)))
+    _count()
+    return out
+
+
+class _PerturbFn(torch.autograd.Function):
+    """a*x + b*noise as a differentiable op (forward du_perturb, backward a*g / b*g by du_perturb's scale form): the re-noising
+    of the gradient schedulers, whose model input stays on the autograd graph (SU/scheduling_ddim_uncertainty_grad.py:522-531)."""
+
+    @staticmethod
+    def forward(ctx, x, noise, a, b):
+        ctx.a, ctx.b = float(a), float(b)
+        return perturb(x.detach(), noise.detach(), a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        gx = scale(g, ctx.a) if ctx.needs_input_grad[0] else None
+        gn = scale(g, ctx.b) if ctx.needs_input_grad[1] else None
+        return gx, gn, None, None
+
+
+def perturb_autograd(x: torch.Tensor, noise: torch.Tensor, a: float, b: float) -> torch.Tensor:
+    return _PerturbFn.apply(x, noise, a, b)
+
+
+class _PerturbFreshFn(torch.autograd.Function):
+    """a*x + b*randn_like(noise_like), differentiable in x, the draw made inside the kernel when it can be (perturb_fresh)."""
+
+    @staticmethod
+    def forward(ctx, x, a, b, noise_like):
+        ctx.a = float(a)
+        return perturb_fresh(x.detach(), a, b, noise_like=noise_like)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (scale(g.contiguous(), ctx.a) if ctx.needs_input_grad[0] else None), None, None, None
+
+
+def perturb_fresh_autograd(x: torch.Tensor, a: float, b: float, noise_like: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _PerturbFreshFn.apply(x, a, b, noise_like)
+
+
+def ema_update(momentum: Optional[torch.Tensor], u: torch.Tensor, beta: float, step: int):
+    """(momentum', momentum' / (1 - beta**step + 1e-5), sqrt of that) in one launch (du_ema_update) —
+    PU/pipeline_sampler_class_conditional_uncertainty_guided_second_order.py:212-218.  momentum None: first step."""
+    _require_cuda(u, "u")
+    u = u if u.is_contiguous() else u.contiguous()
+    if momentum is not None:
+        _require_cuda(momentum, "momentum")
+        momentum = momentum.to(torch.float32).contiguous()
+        if momentum.numel() != u.numel():
+            raise ValueError("ema_update: momentum and map differ in size")
+    new = torch.empty(u.shape, device=u.device, dtype=torch.float32)
+    corrected, root = torch.empty_like(new), torch.empty_like(new)
+    if u.numel() == 0:
+        return new, corrected, root
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else NULL  # noqa: E731
+    L.check(L.load().du_ema_update(p(momentum), p(u), _DT[u.dtype], float(beta), float(1 - beta), float(1 - beta ** step + 1e-5),
+                                   u.numel(), p(new), p(corrected), p(root), _stream(u)))
+    _count()
+    return new, corrected, root
 
 
 def dpm_solver_update(sample: torch.Tensor, m0: torch.Tensor, m1: Optional[torch.Tensor], a: float, b: float, c: float = 0.0,
@@ -690,8 +817,8 @@ class FusedStep:
     marshalling.  Outputs live in `self.res` (dict u, thr, prev, x0, eps, mask) and are overwritten by every
     launch; `set_map_out()` re-targets the map at another slot of the accumulation buffer (F8)."""
 
-    def __init__(self, scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,
-                 coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
+    def __init__(self, scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: Optional[torch.Tensor], q: float,
+                 coeffs: Optional[L.DdimCoeffs], alpha_hat_t: float, moments_mode: str = "var_with_center",
                  S: Optional[torch.Tensor] = None, S_broadcast: bool = False, higher: bool = True,
                  map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
                  want_eps: bool = False, want_mask: bool = False, post_M: Optional[float] = None,
@@ -701,18 +828,22 @@ class FusedStep:
             raise ValueError(f"fused step: M={M} must be in [1, {L.DU_MAX_M}]")
         rows = [Rows(t, f"scores[{k}]") for k, t in enumerate(scores)]
         r0 = rows[0]
-        e, sm = Rows(eps, "eps"), Rows(sample, "sample")
+        skip = sample is None       # skip_ddim: the step ends with the guided score (res["eps"]); no sample, no x_{t-1}
+        e = Rows(eps, "eps")
+        sm = None if skip else Rows(sample, "sample")
         for r in rows[1:] + [e]:
             _same_rows(r0, r, "fused step")
             if r.dt != r0.dt or r.stride != (r0.stride if r is not e else r.stride):
                 raise RuntimeError("fused step: scores and eps must share dtype (and scores one row stride)")
-        _same_rows(r0, sm, "fused step(sample)")
         P = L.FusedParams()
         for k, r in enumerate(rows):
             P.scores[k] = r.ptr.value
         P.M, P.score_dtype, P.score_stride = M, r0.dt, r0.stride
         P.eps, P.eps_stride = e.ptr, e.stride
-        P.sample, P.sample_stride, P.sample_dtype = sm.ptr, sm.stride, sm.dt
+        if not skip:
+            _same_rows(r0, sm, "fused step(sample)")
+            P.sample, P.sample_stride, P.sample_dtype = sm.ptr, sm.stride, sm.dt
+        P.skip_ddim = int(skip)
         P.moments_mode = _MODES[moments_mode]
         self._keep = [rows, e, sm]
         if S is not None:
@@ -729,22 +860,21 @@ class FusedStep:
         P.higher, P.q, P.lerp_fma = int(higher), float(q), int(bool(lerp_fma))
         P.post_M = float(M if post_M is None else post_M)
         P.inv_alpha_hat = float(1.0 / alpha_hat_t)
-        P.ddim = coeffs
+        if coeffs is not None:
+            P.ddim = coeffs
+        elif not skip:
+            raise ValueError("fused step: DDIM coefficients are required unless sample is None (skip_ddim)")
         P.B, P.n = r0.B, r0.n
         dev, shape = eps.device, eps.shape
-        out_dtype = torch.promote_types(torch.promote_types(eps.dtype, sample.dtype), torch.float32)
+        out_dtype = torch.promote_types(torch.promote_types(eps.dtype, eps.dtype if skip else sample.dtype), torch.float32)
         self.P, self._r0, self._dev_tensor = P, r0, eps
         thr = torch.empty(r0.B, device=dev, dtype=torch.float32)
         P.thr_out = C.c_void_p(thr.data_ptr())
-        res = {"u": None, "thr": thr, "x0": None, "eps": None, "mask": None}
-        if prev_out is None:
-            prev_out = torch.empty(shape, device=dev, dtype=out_dtype)
-        pr = Rows(prev_out, "prev_out")
-        if pr.t is not prev_out or prev_out.dtype != out_dtype:
-            raise ValueError(f"fused step: prev_out must be a {out_dtype} tensor with contiguous rows")
-        _same_rows(r0, pr, "fused step(prev_out)")
-        res["prev"] = prev_out
-        P.prev_out, P.prev_stride, P.prev_dtype = pr.ptr, pr.stride, _DT[out_dtype]
+        res = {"u": None, "thr": thr, "x0": None, "eps": None, "mask": None, "prev": None}
+        if skip:
+            want_x0, want_eps = False, True
+        else:
+            self.set_prev_out(prev_out if prev_out is not None else torch.empty(shape, device=dev, dtype=out_dtype), res)
         if want_x0:
             res["x0"] = torch.empty(shape, device=dev, dtype=out_dtype)
             P.x0_out, P.x0_stride = C.c_void_p(res["x0"].data_ptr()), r0.n
@@ -758,6 +888,15 @@ class FusedStep:
         self.set_map_out(map_out if map_out is not None else torch.empty(shape, device=dev, dtype=torch.float32))
         self._fn = L.load().du_fused_uncertainty_step
         self._ref = C.byref(P)
+
+    def set_prev_out(self, prev_out: torch.Tensor, res=None):
+        """Re-target x_{t-1} (a sampling loop hands the step the tensor its next model call reads)."""
+        pr = Rows(prev_out, "prev_out")
+        if pr.t is not prev_out or prev_out.dtype != torch.float32:
+            raise ValueError("fused step: prev_out must be a float32 tensor with contiguous rows")
+        _same_rows(self._r0, pr, "fused step(prev_out)")
+        (self.res if res is None else res)["prev"] = prev_out
+        self.P.prev_out, self.P.prev_stride, self.P.prev_dtype = pr.ptr, pr.stride, L.F32
 
     def set_map_out(self, u: torch.Tensor):
         ur = Rows(u, "map_out")
@@ -803,15 +942,15 @@ def _fused_eligible(scores, eps, sample, map_out, S) -> bool:
     if n == 0 or eps.dtype not in _DT or not fused_supported(n, eps.dtype):
         return False
     vec = 4 if eps.dtype == torch.float32 else 8
-    ts = list(scores) + [eps, sample] + ([map_out] if map_out is not None else []) + ([S] if S is not None else [])
+    ts = list(scores) + [eps] + [t for t in (sample, map_out, S) if t is not None]
     for t in ts:
         if t.data_ptr() % 16 or (t.dim() > 1 and t.shape[0] > 1 and t.stride(0) % vec) or not t[0].is_contiguous():
             return False
     return all(s.dtype == eps.dtype for s in scores) and eps.shape[0] <= 65535
 
 
-def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: torch.Tensor, q: float,
-                     coeffs: L.DdimCoeffs, alpha_hat_t: float, moments_mode: str = "var_with_center",
+def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: Optional[torch.Tensor], q: float,
+                     coeffs: Optional[L.DdimCoeffs], alpha_hat_t: float, moments_mode: str = "var_with_center",
                      sum_source: Optional[torch.Tensor] = None, batch_sum: bool = True, higher: bool = True,
                      map_out: Optional[torch.Tensor] = None, lerp_fma: bool = False, want_x0: bool = False,
                      want_eps: bool = False, want_mask: bool = False, fused: Optional[bool] = None,
@@ -821,9 +960,13 @@ def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: 
     SU/...zigzag_centered.py:472-510.  Returns dict(u, thr, prev, x0, eps, mask).
     batch_sum=True reproduces the reference's `sum(dim=0)` over the batch axis (identity at B=1); `precomputed_sum` is that
     row when the caller already has it (image chunks of a larger batch, or the all-reduced row under batch sharding).
-    fused=None picks the single-launch cluster kernel whenever the shape/alignment allows it."""
+    fused=None picks the single-launch cluster kernel whenever the shape/alignment allows it.
+    sample None: the step ends with the guided score (`eps` in the result; du_fused_params::skip_ddim) — the body of
+    get_uncertainty_guided_score_with_percentile, whose caller applies its own scheduler."""
+    global last_step_path
     M = len(scores)
-    for t in list(scores) + [eps, sample]:
+    skip = sample is None
+    for t in list(scores) + [eps] + ([] if skip else [sample]):
         _require_cuda(t, "uncertainty_step input")
     src = eps if sum_source is None else sum_source
     S, bcast, summed_here = (None if sum_source is None else src), False, False
@@ -833,6 +976,7 @@ def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: 
         S, bcast, summed_here = batch_sum_fn(src), True, True
     if fused is None:
         fused = _fused_eligible(scores, eps, sample, map_out, S)
+    last_step_path = "fused" if fused else "unfused"
     if fused:
         # (the fused launch directly follows the du_batch_sum above on this stream: it may start as its dependent launch)
         return fused_uncertainty_step(scores, eps, sample, q, coeffs, alpha_hat_t, moments_mode=moments_mode, S=S,
@@ -841,11 +985,11 @@ def uncertainty_step(scores: Sequence[torch.Tensor], eps: torch.Tensor, sample: 
     u = moments(scores, center=eps, mode=moments_mode, out=map_out)
     thr = quantile_threshold(u, q, lerp_fma=lerp_fma)
     r = guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=src if S is None else S, aux_broadcast=bcast,
-                    higher=higher, post_M=float(M), inv_alpha_hat=float(1.0 / alpha_hat_t), want_prev=True, want_x0=want_x0,
-                    want_eps=want_eps, want_mask=want_mask)
+                    higher=higher, post_M=float(M), inv_alpha_hat=float(1.0 / alpha_hat_t), want_prev=not skip,
+                    want_x0=want_x0 and not skip, want_eps=want_eps or skip, want_mask=want_mask)
     r["u"], r["thr"] = u, thr
-    if prev_out is not None:
-        prev_out.copy_(r["prev"])
+    if prev_out is not None and not skip:
+        accumulate_slot(r["prev"], prev_out)
         r["prev"] = prev_out
     return r
 

@@ -1,2 +1,144 @@
-"""Module-name alias of the reference's pipeline_uncertainty/pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution.py for the functions on the uncertainty path."""
+"""Drop-in for diffusion_uncertainty/pipeline_uncertainty/pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution.py:
+the module-level `calculate_threshold_map` (:10-30) and `estimate_score_update_posterior` (:32-68) and the pipeline class
+`DiffusionClassConditionalGuidedPosteriorDistribution` (:71-243).
+
+Per window step the reference runs (:141-162): a plain scheduler step, M re-noised forwards (F7), the unbiased variance over the
+M predictions plus the original score (F1c), the per-image percentile mask (F2a) or a fitted tensor threshold (F2b), the
+posterior score blended under the mask (F5) and the scheduler step again on the guided score (F3).  Here everything after the
+forwards is ONE launch — `du_fused_uncertainty_step` through `ops.uncertainty_step` (plus the batch-axis sum that precedes it
+as its dependent launch) — whenever the threshold is a percentile and the scheduler is a plain DDIM scheduler; tensor
+thresholds and other schedulers run the three-kernel chain / the scheduler's own `step()`.
+
+Two defects of the reference class are not reproduced: its `__call__` invokes the four-argument module
+function `calculate_threshold_map` with three arguments (:159; a TypeError under beartype), and the driving script passes a
+`threshold_type` keyword the constructor does not accept (scripts/generate_images_with_uncertainty_threshold.py:212).  The
+constructor takes `threshold_type` (default 'higher', what the class's own method form computes, :194-199).  What IS kept:
+`alpha_hat_t = alphas_cumprod[i]` indexed by the STEP number (:151), the window test `start + num >= i >= start` (:153) and the
+posterior's batch-axis sum of the LAST perturbed prediction (:236).
+"""
+from __future__ import annotations
+
+from math import sqrt
+from typing import Dict, Optional, Union
+
+import torch
+
+from .. import ops
+from ..generate_samples import predict_model
+from ._guided_common import class_names, ddim_coeffs, finish, start_batch
 from .threshold_guidance import calculate_threshold_map, estimate_score_update_posterior  # noqa: F401
+
+
+def _plain_ddim(scheduler) -> bool:
+    """True when `scheduler.step()` is the bare deterministic DDIM update (no window of its own, no noise draw): the window step
+    may then skip the calls to `step()` and run the fused kernel.  This package's DDIMScheduler, or diffusers' by name."""
+    return type(scheduler).__name__ == "DDIMScheduler"
+
+
+class DiffusionClassConditionalGuidedPosteriorDistribution:
+
+    def __init__(self, model, scheduler, threshold: Union[torch.Tensor, float], image_size: int, device: torch.device, batch_size: int,
+                 init_seed_rng: int, fid_evaluator: Optional[object] = None, M: int = 5, threshold_type: str = "higher"):
+        assert isinstance(threshold, (torch.Tensor, float)), "Threshold must be a tensor or a float"
+        if isinstance(threshold, float):
+            assert 0 <= threshold <= 1, "Threshold percentile must be between 0 and 1"
+        self.model = model
+        self.scheduler = scheduler
+        self.threshold = threshold
+        self.image_size = image_size
+        self.device = torch.device(device)
+        self.fid_evaluator = fid_evaluator
+        self.batch_size = batch_size
+        self.is_uvit = "UViTAE" in class_names(model)
+        self.init_seed_rng = init_seed_rng
+        self.M = M
+        self.lambda_update = 7
+        self.threshold_type = threshold_type
+        self.fused_steps = 0          # window steps that ran as the single fused launch (tests / benchmarks read it)
+
+    def __call__(self, num_samples: Optional[int] = None, num_classes: Optional[int] = None, X_T: Optional[torch.Tensor] = None,
+                 y: Optional[torch.Tensor] = None, start_step: int = 0, num_steps: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        assert num_samples is not None or X_T is not None, "Either num_samples or X_T must be provided"
+        assert num_classes is not None or y is not None, "Either num_classes or y must be provided"
+        if self.device.type != "cuda":
+            raise RuntimeError(f"device {self.device}: the uncertainty path has no CPU fallback")
+        sched = self.scheduler
+        num_generated_samples = 0
+        samples_x_t, samples_y, samples_gen_images = [], [], []
+        if num_steps is None:
+            num_steps = sched.timesteps.shape[0] - start_step
+        if num_samples is None:
+            num_samples = X_T.shape[0]
+        if isinstance(self.threshold, torch.Tensor):
+            assert self.threshold.shape[0] == sched.timesteps.shape[0], f'{self.threshold.shape=} {sched.timesteps.shape=}'
+        sched.config.after_step = start_step
+        sched.config.num_steps_uc = num_steps
+        sched.set_timesteps(len(sched.timesteps))
+        generator = torch.Generator(device=self.device)
+        plain = _plain_ddim(sched)
+        i_batch = 0
+        while num_samples > num_generated_samples:
+            input, y_slice = start_batch(X_T, y, num_classes, num_generated_samples, self.batch_size, 3, self.image_size, self.device,
+                                         generator, self.init_seed_rng + i_batch)
+            samples_x_t.append(input.cpu().clone())
+            samples_y.append(y_slice)
+            sched.prompt_embeds = y_slice
+            with torch.no_grad():
+                for i, t in enumerate(sched.timesteps.tolist()):
+                    t_tensor = torch.full((y_slice.shape[0],), t, device=self.device, dtype=torch.long)
+                    noisy_residual = predict_model(self.model, input, t_tensor, y_slice)
+                    in_window = (start_step + num_steps) >= i >= start_step
+                    if not in_window:
+                        input = sched.step(noisy_residual, t, input).prev_sample
+                        continue
+                    alpha_hat_t = sched.alphas_cumprod[i]
+                    input = self.window_step(input, y_slice, i, t, t_tensor, noisy_residual, alpha_hat_t, plain)
+            gen_images = ops.image_uint8(input)
+            num_generated_samples += gen_images.shape[0]
+            if self.fid_evaluator is not None:
+                self.fid_evaluator.update(gen_images, real=False)
+            samples_gen_images.append(gen_images)
+            i_batch += 1
+        return finish(samples_y, samples_x_t, sched, samples_gen_images, self.fid_evaluator)
+
+    # ------------------------------------------------------------------------------------------------ the window step
+    def perturbed_predictions(self, input, y_slice, t_tensor, noisy_residual, alpha_hat_t):
+        """F7 + the M forwards (:222-227): x0 = (x - sqrt(1-a) eps) / sqrt(a); x_hat = sqrt(a) x0 + sqrt(1-a) n, the draw made inside
+        the perturbation kernel (torch's Philox stream, bit for bit)."""
+        sa, sb = sqrt(alpha_hat_t), sqrt(1 - alpha_hat_t)          # math.sqrt of the 0-dim tensors, as the reference
+        c_x0 = ops.make_coeffs(sa, sb, 0.0, 0.0, clip_sample=False)
+        x0 = ops.ddim_step(noisy_residual, input, c_x0, want_prev=False, want_x0=True)[1]
+        return [predict_model(self.model, ops.perturb_fresh(x0, sa, sb, noise_like=input), t_tensor, y_slice) for _ in range(self.M)]
+
+    def window_step(self, input, y_slice, i, t, t_tensor, noisy_residual, alpha_hat_t, plain: Optional[bool] = None):
+        """x_{t-1} of one in-window step (:141-162)."""
+        sched = self.scheduler
+        plain = _plain_ddim(sched) if plain is None else plain
+        if not plain:
+            sched.step(noisy_residual, t, input)      # the reference's first step(): an uncertainty scheduler draws noise / runs its window here
+        preds = self.perturbed_predictions(input, y_slice, t_tensor, noisy_residual, alpha_hat_t)
+        coeffs = ddim_coeffs(sched, t) if plain else None
+        if coeffs is not None and isinstance(self.threshold, float):
+            r = ops.uncertainty_step(preds, noisy_residual, input, self.threshold, coeffs, alpha_hat_t, moments_mode="var_with_center",
+                                     sum_source=preds[-1], batch_sum=True, higher=self.threshold_type == "higher")
+            self.fused_steps += int(ops.last_step_path == "fused")
+            return r["prev"]
+        u = ops.moments(preds, center=noisy_residual, mode="var_with_center", out_dtype=preds[0].dtype)
+        mask = calculate_threshold_map(self.threshold, i, u, self.threshold_type)
+        S = ops.batch_sum(preds[-1])
+        guided = ops.guided_step(noisy_residual, input if coeffs is not None else None, coeffs, guidance="posterior", u=u, mask=mask,
+                                 aux=S, aux_broadcast=True, post_M=float(self.M),
+                                 inv_alpha_hat=float(1 / torch.as_tensor(alpha_hat_t, dtype=torch.float32)),
+                                 want_prev=coeffs is not None, want_eps=coeffs is None)
+        if coeffs is not None:
+            return guided["prev"]
+        return sched.step(guided["eps"], t, input).prev_sample
+
+    def calculate_threshold_map(self, i, pixel_wise_uncertainty):
+        """The method form (:194-199): `higher`, no fp32 cast in the reference — the kernels always compare in fp32."""
+        return calculate_threshold_map(self.threshold, i, pixel_wise_uncertainty, "higher")
+
+    def estimate_score_update(self, input, y_slice, i, t_tensor, noisy_residual, prev_noisy_sample, alpha_hat_t):
+        """(pixel_wise_uncertainty, new_score) — :201-237."""
+        return estimate_score_update_posterior(self.M, self.model, self.scheduler, input, y_slice, t_tensor, noisy_residual,
+                                               prev_noisy_sample, alpha_hat_t, predict=lambda x, tt, yy: predict_model(self.model, x, tt, yy))

@@ -121,6 +121,7 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
         self.timestep_after_step = None
         self.timestep_end_step = None
         self.map_sink = None            # optional UncertaintyMapAccumulator (F8): maps are written straight into its slots
+        self.map_in_sink = False        # whether the LAST in-window step wrote its map into the sink (else the caller stashes it)
         self._scalar_cache: Dict[Tuple, Tuple] = {}
 
     # ------------------------------------------------------------------------------------------ plain DDIM API
@@ -212,6 +213,7 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
         st = StepState(model_output=model_output, sample=sample, t=t, prev_t=host["prev_t"], eta=eta,
                        use_clipped=use_clipped_model_output, coeffs=coeffs, host=host, prev=None, x0=None, eps=None)
 
+        self.map_in_sink = False
         pre = self._before_update(st) if window else None   # MC-dropout samples before the update (RNG order)
 
         best_noise = torch.randn_like(sample if sample.dtype.is_floating_point else model_output) if self.draws_best_noise else None
@@ -284,8 +286,13 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
 
     def _map_out(self, like: torch.Tensor, dtype: torch.dtype = torch.float32) -> Optional[torch.Tensor]:
         """Destination of this step's map: the next slot of the attached accumulation buffer (F8 fused) or None."""
-        if self.map_sink is None:
+        self.map_in_sink = False
+        if self.map_sink is None or not self.map_sink.accepts(like.shape, dtype):
+            # no sink, or a map the sink's slots cannot hold as they are (fp16 / bf16 maps of the `var` modes under autocast,
+            # the [B,1,H,W] map of flip_threshold): the step returns a fresh tensor with the reference's dtype and shape and
+            # the sampling loop stashes it (du_accumulate_slot converts)
             return None
+        self.map_in_sink = True
         return self.map_sink.next_slot(like.shape, dtype)
 
     def _perturbed_input(self, st: StepState, base_x0: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:

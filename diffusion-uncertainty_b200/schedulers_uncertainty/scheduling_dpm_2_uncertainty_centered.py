@@ -110,6 +110,7 @@ class KDPM2DiscreteSchedulerUncertainty(ConfigurableScheduler):   # structurally
         self.timestep_after_step = None
         self.timestep_end_step = None
         self.map_sink = None        # optional UncertaintyMapAccumulator: maps go straight into its slots (F8)
+        self.map_in_sink = False    # whether the last in-window step wrote its map there (else the caller stashes it)
 
     # ------------------------------------------------------------------------------------------------ schedule
     @property
@@ -245,7 +246,8 @@ class KDPM2DiscreteSchedulerUncertainty(ConfigurableScheduler):   # structurally
             x_t_hat = ops.perturb_fresh(pred_original_sample, sa, sb)     # `noise = torch.randn_like(...)` drawn in the kernel
             x_t_hat = self.scale_model_input(x_t_hat, timestep)
             scores.append(self.predict_model(x_t_hat, timestep))
-        out = self.map_sink.next_slot(scores[0].shape, torch.float32) if self.map_sink is not None else None
+        self.map_in_sink = self.map_sink is not None and self.map_sink.accepts(scores[0].shape, torch.float32)
+        out = self.map_sink.next_slot(scores[0].shape, torch.float32) if self.map_in_sink else None
         uncertainty = ops.moments(scores, center=model_output, mode="centered", out=out, out_dtype=torch.float32)
         return uncertainty, pred_original_sample
 

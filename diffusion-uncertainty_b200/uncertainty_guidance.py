@@ -66,6 +66,11 @@ def _forward(model, model_type, x_hat, t_tensor, y, guidance_scale, extra):
     return predict_model_stable_diffusion(model, x_hat, t_tensor, y, guidance_scale, extra_diffusion_kwargs=extra), t_tensor
 
 
+def _as_rows(eps: Tensor, like: Tensor) -> Tensor:
+    """the centre in the dtype of the predictions (the fused kernel reads scores and centre through one vector type)"""
+    return eps if eps.dtype == like.dtype else eps.to(like.dtype)
+
+
 def _rows_like(t: Tensor, ref: Tensor) -> Tensor:
     """Broadcast along the batch axis without copying (the CFG-doubled latent meets the single guided score)."""
     return t if t.shape == ref.shape else t.expand(ref.shape)
@@ -90,12 +95,10 @@ def get_uncertainty_guided_score_with_percentile(pred_epsilon: Tensor, input: Te
                 x_hat = ops.perturb_fresh(x0, sa, sb, noise_like=pred_epsilon)     # `torch.randn_like(pred_epsilon)` drawn in the kernel
                 out, t_tensor = _forward(model, model_type, x_hat, t_tensor, y, guidance_scale, extra_diffusion_kwargs)
                 preds.append(out)
-            u = ops.moments(preds, center=pred_epsilon, mode="var_with_center", out_dtype=preds[0].dtype)
-            thr = ops.quantile_threshold(u, percentile)
-            B = pred_epsilon.shape[0]
-            S = ops.batch_sum(pred_epsilon) if B > 1 else pred_epsilon        # `pred_epsilon.sum(dim=0)` (:116)
-            r = ops.guided_step(pred_epsilon, None, None, guidance="posterior", u=u, thr=thr, aux=S, aux_broadcast=B > 1,
-                                post_M=float(M), inv_alpha_hat=float(1 / a), want_eps=True)
+            # F1c -> F2a -> F5 as ONE launch (du_fused_uncertainty_step with skip_ddim; the batch-axis sum `pred_epsilon.sum(dim=0)`,
+            # :116, precedes it as its dependent launch when B > 1); shapes the fused kernel does not take run the three-kernel chain
+            r = ops.uncertainty_step(preds, _as_rows(pred_epsilon, preds[0]), None, percentile, None, a, moments_mode="var_with_center",
+                                     batch_sum=True)
             return r["eps"]
 
     # ---- gradient form: the objective and its backward stay in autograd
@@ -107,11 +110,10 @@ def get_uncertainty_guided_score_with_percentile(pred_epsilon: Tensor, input: Te
             x_hat = sa * pred_x_0 + sb * torch.randn_like(pred_epsilon)
             out, t_tensor = _forward(model, model_type, x_hat, t_tensor, y, guidance_scale, extra_diffusion_kwargs)
             preds.append(out)
-        stacked = torch.stack(preds, dim=0)
-        objective = torch.var(stacked, dim=0).mean(dim=0).sum()
-        objective.backward()
+        u = ops.moments_autograd(preds, "var")          # torch.var(stack(preds), 0) and its backward: du_moments / du_moments_backward
+        u.mean(dim=0).sum().backward()
     with torch.no_grad():
-        u = ops.moments([p.detach() for p in preds], mode="var", out_dtype=preds[0].dtype)
+        u = u.detach()
         thr = ops.quantile_threshold(u, percentile)
         assert pred_epsilon.grad is not None
         r = ops.guided_step(pred_epsilon.detach(), None, None, guidance="grad_add", u=u, thr=thr, aux=pred_epsilon.grad,

@@ -50,7 +50,9 @@ enum du_status {
 const char* du_last_error(void);
 int du_version(void);            /* ABI version, currently 1 */
 int du_num_sms(int device);      /* SM count of `device` (148 on B200); <0 on error */
-int du_set_device(int device);   /* make `device` current for this thread's subsequent calls (one process per GPU) */
+/* Select the device the calling THREAD's subsequent calls run on (thread-local; < 0 = whatever device is current).  The CUDA
+ * current device of the caller is never changed: each call switches for its own duration and restores it on return. */
+int du_set_device(int device);
 
 /* ------------------------------------------------------------------------------------------------
  * F1 — reduction over the M axis.
@@ -174,6 +176,8 @@ int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_dtype,
  *   GRAD_ADD   uncertainty_guidance.py:129             eps + lam*g*m
  *   WEIGHTS    SU/scheduling_ddim_uncertainty_threshold.py:554-574   eps*w; x0 from the UNMASKED eps
  *   LINCOMB    SU/scheduling_ddim_mc_dropout_gradient.py:514         post_M*eps + lam*g   (post_M carries the eps weight)
+ *   SIGN_ADD   PU/..._guided_second_order.py:249                     eps + u * sign(n) * m   (aux = the normal draw n)
+ *   MUL_BLEND  generate_samples.py:953                               eps(1-m) + eps*m*g
  *   NONE       plain F3
  * x0_unguided != 0: x0 is computed from the UNGUIDED eps and only the direction term uses eps' — what every in-scheduler
  * guidance of the reference does (SU/scheduling_ddim_uncertainty_grad.py:551-570, ..._mc_dropout_gradient.py:514-515,
@@ -182,7 +186,7 @@ int du_ddim_step(const void* model_output, int64_t mo_stride, int mo_dtype,
  * mask/weight tensor.
  * ---------------------------------------------------------------------------------------------- */
 enum du_guidance { DU_GUIDE_NONE = 0, DU_GUIDE_POSTERIOR = 1, DU_GUIDE_GRAD_BLEND = 2, DU_GUIDE_GRAD_ADD = 3, DU_GUIDE_WEIGHTS = 4,
-                   DU_GUIDE_LINCOMB = 5 };
+                   DU_GUIDE_LINCOMB = 5, DU_GUIDE_SIGN_ADD = 6, DU_GUIDE_MUL_BLEND = 7 };
 
 typedef struct du_guided_params {
   /* inputs */
@@ -222,7 +226,19 @@ int du_batch_sum(const void* x, int64_t x_stride, int x_dtype, int64_t B, int64_
  * ---------------------------------------------------------------------------------------------- */
 int du_perturb(const void* x, int64_t x_stride, int x_dtype, const void* noise, int64_t noise_stride,
                int noise_dtype, float a, float b, int64_t B, int64_t n, void* out, int64_t out_stride,
-               int out_dtype, du_stream_t stream);
+               int out_dtype, du_stream_t stream);   /* noise == NULL: out = a*x */
+/* The same with one (a, b) pair PER ROW, read from device vectors a_rows[B], b_rows[B] — add_noise / get_velocity called with a
+ * vector of per-sample timesteps (SU/scheduling_ddim_uncertainty_zigzag_centered.py:606-626, 629-646). */
+int du_perturb_rows(const void* x, int64_t x_stride, int x_dtype, const void* noise, int64_t noise_stride,
+                    int noise_dtype, const float* a_rows, const float* b_rows, int64_t B, int64_t n, void* out,
+                    int64_t out_stride, int out_dtype, du_stream_t stream);
+
+/* Second-order momentum of the map (PU/pipeline_sampler_class_conditional_uncertainty_guided_second_order.py:212-218):
+ *   m' = momentum ? beta*momentum + one_minus_beta*u : u;   corrected = m' / denom;   root = sqrt(corrected)
+ * over N contiguous elements (momentum fp32, nullable on the first step; corrected_out / sqrt_out nullable).  The host passes
+ * denom = 1 - beta**i + 1e-5 and one_minus_beta = 1 - beta, both evaluated in double like the reference's Python scalars. */
+int du_ema_update(const float* momentum, const void* u, int u_dtype, float beta, float one_minus_beta, float denom, int64_t N,
+                  float* momentum_out, float* corrected_out, float* sqrt_out, du_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * F7 + N1 — the same combination with the noise drawn in the kernel:
@@ -285,6 +301,10 @@ typedef struct du_fused_params {
   void* x0_out;         int64_t x0_stride;      /* nullable, prev_dtype                              */
   void* eps_out;        int64_t eps_out_stride; /* nullable, fp32                                    */
   float* mask_out;      int64_t mask_out_stride;/* nullable                                          */
+  int32_t skip_ddim;    int32_t _reserved0;     /* skip_ddim != 0: stop after the posterior blend — eps_out (required) receives the
+                                                 * guided score, sample / prev_out / x0_out are ignored (may be NULL).  This is the
+                                                 * whole body of get_uncertainty_guided_score_with_percentile (uncertainty_guidance.py:
+                                                 * 99-120), whose caller applies its own scheduler afterwards.                      */
 } du_fused_params;
 
 /* returns DU_ERR_TOO_LARGE when a row does not fit the cluster's shared memory (use the unfused calls) */
@@ -324,7 +344,7 @@ int du_flip_sqdiff(const void* eps, int64_t eps_stride, int eps_dtype, const voi
  * (`uncertainty.mean(dim=0).sum().backward()`: SU/scheduling_ddim_uncertainty_grad.py:536-538,
  * SU/scheduling_ddim_mc_dropout_gradient.py:499-503, SU/scheduling_ddim_model_gradient_guided.py:546-548,
  * PU/pipeline_sampler_class_conditional_uncertainty_guided_gradient.py:190-194).  grad_scores[m] = grad_u * d u / d s_m for
- * modes VAR_UNBIASED, CENTERED, VAR_WITH_CENTER; grad_center (nullable) = grad_u * d u / d center.  grad_scores[m] may be
+ * modes VAR_UNBIASED, STD_UNBIASED (generate_samples.py:941-943), CENTERED, VAR_WITH_CENTER; grad_center (nullable) = grad_u * d u / d center.  grad_scores[m] may be
  * NULL for samples that need no gradient.  The score model's own backward stays torch autograd.
  * ---------------------------------------------------------------------------------------------- */
 int du_moments_backward(const void* const* scores, int M, int64_t score_stride, int score_dtype, const void* center,
