@@ -161,34 +161,211 @@ def time_cpu(workload, sample_images, budget_s, min_reps=2):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (torch eager expressions, restated in
-    oracle/du_oracle.py and pinned bit-exact to the reference by tests/golden) on the box's host cores."""
+    oracle/du_oracle.py and pinned bit-exact to the reference by tests/golden) on the box's host cores, on the SAME
+    configuration as the GPU arm: the whole batch of the workload per step.  (The reference cannot be pip-installed here — its
+    build backend, hatchling, is not in the wheelhouse — and the arithmetic of this path is inline in functions that also call
+    the score model, so the port is what is timed)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     B, C, H, W, M, q = WORKLOADS[args.workload]
-    b = min(B, 16)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    eps, scores, sample = synth_host(b, C, H, W, M, torch.float32, 1234, pin=False)
-    step = cpu_step_fn(b, C, H, W, M, q)
+    eps, scores, sample = synth_host(B, C, H, W, M, torch.float32, 1234, pin=False)
+    step = cpu_step_fn(B, C, H, W, M, q)
     for _ in range(max(1, min(args.warmup, 3))):
         step(eps, scores, sample)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step(eps, scores, sample)
     dt = time.perf_counter() - t0
-    val = b * H * W * args.steps / dt / 1e6
+    val = B * H * W * args.steps / dt / 1e6
     line = {"impl": "reference", "metric": "uncertainty_step_throughput", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "batch_per_gpu": B, "M": M, "q": q, "sample_images_per_step": b},
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": step_config(args.workload, B, world, True, "f32"),
             "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port",
-                             "sample": f"{b} of {B} images per step, torch {torch.__version__} CPU, {cores} threads"},
+                             "sample": f"all {B} images of {args.workload} per step, {args.steps} steps, torch {torch.__version__} CPU, "
+                                       f"{cores} threads"},
             "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def step_config(workload, B_total, world, batch_sum, dtype_tag):
+    """`config` of a step line — the same keys and values in both arms."""
+    _, C, H, W, M, q = WORKLOADS[workload]
+    return {"workload": workload, "global_batch": B_total, "shape": [C, H, W], "M": M, "q": q, "score_dtype": dtype_tag,
+            "chain": "F1c var(M+1) -> F2a quantile mask -> F5 posterior -> F3 DDIM (+F8 slot write)", "batch_sum": bool(batch_sum)}
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
+def eager_reference_step(eps, scores, sample, q, M, sc, batch_sum=True):
+    """The reference's eager torch expressions of the step, on whatever device the tensors live on (no library of this
+    repository involved): uncertainty_guidance.py:101-120 (F1c, F2a, F5) + SU/scheduling_ddim_uncertainty_zigzag_centered.py:
+    472-510 (F3, epsilon prediction, clip_sample).  What a user of the reference runs on the same B200."""
+    pe = eps.float() if eps.dtype != torch.float32 else eps
+    stacked = torch.stack([s.float() if s.dtype != torch.float32 else s for s in scores] + [pe], dim=0)
+    u = torch.var(stacked, dim=0)
+    shp = u.shape
+    thr = torch.quantile(u.flatten(1).to(torch.float32), q, dim=1, keepdim=True).view(shp[0], *([1] * (len(shp) - 1)))
+    mask = (u > thr).float()
+    inv_var = 1 / u
+    post = (1 / (M * inv_var + 1 / sc["alpha_hat"])) * (inv_var * (pe.sum(dim=0) if batch_sum else pe))
+    eg = pe * (1 - mask) + mask * post
+    x0 = ((sample - sc["sqrt_beta_t"] * eg) / sc["sqrt_alpha_t"]).clamp(-1.0, 1.0)
+    prev = sc["sqrt_alpha_prev"] * x0 + sc["dir_coef"] * eg
+    return u, thr.flatten(), mask, prev
+
+
+class StepBench:
+    """One (workload, score dtype, per-GPU batch) instance of the step on a device: resident inputs, the prepared fused launch,
+    CUDA graphs of K steps, parity check and timings."""
+    PREV_RING = 8     # x_{t-1} goes to a ring of buffers (8 x 25 MB at ImageNet-128): the 126 MB L2 cannot absorb the writes
+
+    def __init__(self, ops, workload, dtype_name, B, dev, seed, batch_sum=True, unfused=False):
+        self.ops, self.dev, self.workload, self.dtype_name = ops, dev, workload, dtype_name
+        _, C, H, W, M, q = WORKLOADS[workload]
+        self.B, self.C, self.H, self.W, self.M, self.q, self.batch_sum = B, C, H, W, M, q, bool(batch_sum) and B > 1
+        self.dtype = DTYPES[dtype_name]
+        self.sc = ddim_scalars()
+        self.coeffs = ops.make_coeffs(self.sc["sqrt_alpha_t"], self.sc["sqrt_beta_t"], self.sc["sqrt_alpha_prev"], self.sc["dir_coef"],
+                                      clip_sample=True)
+        self.h = synth_host(B, C, H, W, M, self.dtype, seed, pin=True)
+        h_eps, h_scores, h_sample = self.h
+        self.eps, self.scores, self.sample = h_eps.to(dev), [s.to(dev) for s in h_scores], h_sample.to(dev)
+        self.maps = torch.zeros(B, T_UC, C, H, W, device=dev, dtype=torch.float32)      # F8 accumulation buffer
+        self.S = torch.empty(C, H, W, device=dev, dtype=torch.float32)
+        self.prevs = [torch.empty(B, C, H, W, device=dev, dtype=torch.float32) for _ in range(self.PREV_RING)]
+        self.n_el = B * C * H * W
+        self.sb = 4 if self.dtype == torch.float32 else 2
+        self.fused = (not unfused) and ops.fused_supported(C * H * W, self.dtype) > 0
+        self.plan = None
+        if self.fused:
+            self.plan = ops.FusedStep(self.scores, self.eps, self.sample, q, self.coeffs, self.sc["alpha_hat"],
+                                      S=self.S if self.batch_sum else None, S_broadcast=self.batch_sum, map_out=self.maps[:, 0],
+                                      prev_out=self.prevs[0])
+        self.kernel = "moments_kernel"
+
+    def alg_bytes(self):
+        return algorithmic_bytes_per_element(self.M, self.sb) * self.n_el
+
+    def step(self, i):
+        ops, slot = self.ops, self.maps[:, i % T_UC]
+        if self.fused:
+            self.plan.set_map_out(slot)
+            self.plan.set_prev_out(self.prevs[i % self.PREV_RING])
+            if self.batch_sum:                   # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
+                return self.plan.launch_with_batch_sum(self.eps, self.S)["prev"]      # du_batch_sum, then the step as its dependent launch
+            return self.plan.launch()["prev"]
+        if self.batch_sum:
+            ops.batch_sum(self.eps, out=self.S)
+        u = ops.moments(self.scores, center=self.eps, mode="var_with_center", out=slot)
+        thr = ops.quantile_threshold(u, self.q)
+        r = ops.guided_step(self.eps, self.sample, self.coeffs, guidance="posterior", u=u, thr=thr,
+                            aux=self.S if self.batch_sum else self.eps, aux_broadcast=self.batch_sum, post_M=float(self.M),
+                            inv_alpha_hat=1.0 / self.sc["alpha_hat"], want_eps=False)
+        return r["prev"]
+
+    def kernel_only(self, i):
+        """the dominant kernel alone (roofline.achieved = its algorithmic bytes / its average launch duration)"""
+        if self.fused:
+            self.plan.set_map_out(self.maps[:, i % T_UC])
+            self.plan.set_prev_out(self.prevs[i % self.PREV_RING])
+            self.plan.launch()
+        else:
+            self.ops.moments(self.scores, center=self.eps, mode="var_with_center", out=self.maps[:, i % T_UC])
+
+    def capture(self, fn, steps):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(steps):
+                fn(i)
+        return g
+
+    def warm(self, n):
+        for i in range(n):
+            self.step(i)
+        torch.cuda.synchronize()
+        if self.fused:
+            self.kernel = self.ops.fused_last_kernel() or "fused_step_kernel"
+
+    def parity(self):
+        """The timed configuration once, outside the timed region, against the reference's eager torch expressions on the same
+        device: map within 1e-5 relative, thresholds bit-equal to torch.quantile of the kernel's own map, masks identical away
+        from the threshold (and different on < 0.1 % of the pixels overall), x_{t-1} within 1e-5 of max(|x|, 0.4) where the masks
+        agree.  Returns a dict for the bench line; raises on failure."""
+        prev = self.step(0)
+        u_k = self.maps[:, 0]
+        u, thr, mask, prev_ref = eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum)
+        torch.cuda.synchronize()
+        # relative to max(u, 1e-3 mean(u)): a variance far below the typical one is the difference of nearly equal fp32 numbers,
+        # and no two summation orders agree on it to 1e-5 (torch.var's own error is of that size there)
+        rel_u = float(((u_k - u).abs() / u.abs().clamp_min(1e-3 * float(u.mean()))).max())
+        out = {"map_max_rel_err": rel_u, "map_max_rel_err_unfloored": float(((u_k - u).abs() / u.abs().clamp_min(1e-30)).max())}
+        if rel_u > 1e-5:
+            raise AssertionError(f"parity: map differs from torch.var by {rel_u:.3e} relative")
+        if self.fused:
+            thr_k = self.plan.res["thr"]
+            thr_c = torch.quantile(u_k.flatten(1).cpu(), self.q, dim=1)    # (torch's CUDA lerp contracts to an FMA: compare on the host)
+            out["thr_bit_exact"] = bool(torch.equal(thr_k.cpu(), thr_c))
+            if not out["thr_bit_exact"]:
+                raise AssertionError("parity: thresholds are not bit-identical to torch.quantile of the map")
+            mask_k = (u_k > thr_k.view(-1, 1, 1, 1)).float()
+        else:
+            mask_k = (u_k > thr.view(-1, 1, 1, 1)).float()
+        agree = mask_k == mask
+        out["mask_agreement"] = float(agree.float().mean())
+        near = (u - thr.view(-1, 1, 1, 1)).abs() <= 1e-5 * thr.view(-1, 1, 1, 1).abs()
+        if bool((~agree & ~near).any()) or out["mask_agreement"] < 0.999:
+            raise AssertionError("parity: masks differ away from the threshold")
+        fin = torch.isfinite(prev_ref) & agree
+        err = (prev - prev_ref).abs()[fin]
+        bound = 1e-5 * prev_ref.abs().clamp_min(0.4)[fin]
+        out["prev_max_abs_err"] = float(err.max()) if err.numel() else 0.0
+        if bool((err > bound).any()):
+            raise AssertionError(f"parity: x_(t-1) off by {out['prev_max_abs_err']:.3e}")
+        if not bool(torch.equal(torch.isfinite(prev)[agree], torch.isfinite(prev_ref)[agree])):
+            raise AssertionError("parity: non-finite values in different places")
+        return out
+
+    def time_eager_reference(self, reps=5):
+        """the reference's eager expressions on this GPU, CUDA events, best of `reps` after one warm-up"""
+        best = None
+        for r in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum)
+            e1.record()
+            torch.cuda.synchronize()
+            if r > 0:
+                ms = e0.elapsed_time(e1)
+                best = ms if best is None or ms < best else best
+        return best
+
+    def quick(self, steps):
+        """(ms per step, ms per launch of the dominant kernel) from CUDA graphs of `steps` steps, one warm replay each"""
+        self.warm(3)
+        use_graph = self.fused
+        out = []
+        for fn in (self.step, self.kernel_only):
+            if use_graph:
+                g = self.capture(fn, steps)
+                g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if use_graph:
+                g.replay()
+            else:
+                for i in range(steps):
+                    fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            out.append(e0.elapsed_time(e1) / steps)
+        return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     from diffusion_uncertainty_b200 import ops
@@ -203,78 +380,35 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, C, H, W, M, q = WORKLOADS[args.workload]
-    dtype = DTYPES[args.dtype]
-    n_el = B * C * H * W
-    sc = ddim_scalars()
-    coeffs = ops.make_coeffs(sc["sqrt_alpha_t"], sc["sqrt_beta_t"], sc["sqrt_alpha_prev"], sc["dir_coef"], clip_sample=True)
-
-    h_eps, h_scores, h_sample = synth_host(B, C, H, W, M, dtype, 1234 + rank + args.seed_offset, pin=True)
-    eps, scores, sample = h_eps.to(dev), [s.to(dev) for s in h_scores], h_sample.to(dev)
-    maps = torch.zeros(B, T_UC, C, H, W, device=dev, dtype=torch.float32)   # F8 accumulation buffer
-
-    S_buf = torch.empty(C, H, W, device=dev, dtype=torch.float32)
-    fused = (not args.unfused) and ops.fused_supported(C * H * W, dtype) > 0
-    plan = None
-    if fused:
-        # the prepared single-launch step (ops.FusedStep == du_fused_uncertainty_step): F1c -> F2a -> F5 -> F3 (+F8)
-        plan = ops.FusedStep(scores, eps, sample, q, coeffs, sc["alpha_hat"], S=S_buf if args.batch_sum else None,
-                             S_broadcast=bool(args.batch_sum), map_out=maps[:, 0])
-    dominant = "fused_step_kernel" if fused else "moments_kernel"
-    prev_u = torch.empty(B, C, H, W, device=dev, dtype=torch.float32)
-    u_tmp = torch.empty(B, C, H, W, device=dev, dtype=torch.float32)
-
-    def kernel_only(i):
-        """the dominant kernel alone (roofline.achieved is its algorithmic bytes / its average launch duration)"""
-        if fused:
-            plan.set_map_out(maps[:, i % T_UC])
-            plan.launch()
-        else:
-            ops.moments(scores, center=eps, mode="var_with_center", out=maps[:, i % T_UC])
-
-    def step(i):
-        slot = maps[:, i % T_UC]
-        if fused:
-            plan.set_map_out(slot)
-            if args.batch_sum:                       # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
-                return plan.launch_with_batch_sum(eps, S_buf)["prev"]      # du_batch_sum, then the step as its dependent launch
-            return plan.launch()["prev"]
-        if args.batch_sum:
-            ops.batch_sum(eps, out=S_buf)
-        u = ops.moments(scores, center=eps, mode="var_with_center", out=slot)
-        thr = ops.quantile_threshold(u, q)
-        r = ops.guided_step(eps, sample, coeffs, guidance="posterior", u=u, thr=thr, aux=S_buf if args.batch_sum else eps,
-                            aux_broadcast=bool(args.batch_sum), post_M=float(M), inv_alpha_hat=1.0 / sc["alpha_hat"],
-                            want_eps=False)
-        return r["prev"]
+    B_total, C, H, W, M, q = WORKLOADS[args.workload]
+    # BASELINE.json configs[2]: "batch 128 sharded across 1/2/4/8" — the default for N > 1 is the STRONG split (B_total / N images
+    # per GPU); --scaling weak keeps B_total images on every GPU (N independent replicas of the N=1 job)
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
+    if scaling == "strong" and B_total % world != 0:
+        raise SystemExit(f"--scaling strong needs the batch ({B_total}) to divide over {world} ranks")
+    B = B_total // world if scaling == "strong" else B_total
+    sb_ = StepBench(ops, args.workload, args.dtype, B, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum, unfused=args.unfused)
+    fused = sb_.fused
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        out = step(i)
+    sb_.warm(args.warmup)
     barrier()
-    if fused:
-        dominant = ops.fused_last_kernel() or dominant
+    dominant = sb_.kernel
+    parity = None if args.no_parity else sb_.parity()
+    step, kernel_only = sb_.step, sb_.kernel_only
 
     # The K timed steps are captured into ONE CUDA graph (every C-ABI call is capturable: no host reads, no allocation),
     # so the timed region holds exactly K steps of GPU work and no Python / launch latency between them.  The unfused
     # chain allocates per call and is timed eagerly.
     use_graph = fused and not args.eager
-
-    def capture(fn):
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for i in range(args.steps):
-                fn(i)
-        return g
-
     launches0 = ops.launch_count
     if use_graph:
-        g_step, g_kernel = capture(step), capture(kernel_only)
-        n_step_launches = args.steps * (2 if args.batch_sum else 1)
+        g_step, g_kernel = sb_.capture(step, args.steps), sb_.capture(kernel_only, args.steps)
+        n_step_launches = args.steps * (2 if sb_.batch_sum else 1)
         g_step.replay(); g_kernel.replay()            # one untimed replay each
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -349,14 +483,15 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers (pinned): H2D of the step's inputs and D2H of its results
     # inside the timed region (diffusion_uncertainty_b200.host_step pipelines image chunks over three streams)
     from diffusion_uncertainty_b200.host_step import HostStreamedUncertaintyStep
+    h_eps, h_scores, h_sample = sb_.h
     h_prev = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
     h_map = torch.empty(B, C, H, W, dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
-    host_step = HostStreamedUncertaintyStep(B, (C, H, W), M, dev, score_dtype=dtype, chunks=args.e2e_chunks)
+    host_step = HostStreamedUncertaintyStep(B, (C, H, W), M, dev, score_dtype=sb_.dtype, chunks=args.e2e_chunks)
 
     def e2e_step(i):
-        return host_step(h_scores, h_eps, h_sample, q, coeffs, sc["alpha_hat"], h_prev, h_map, batch_sum=bool(args.batch_sum),
-                         map_slot=maps[:, i % T_UC])
+        return host_step(h_scores, h_eps, h_sample, q, sb_.coeffs, sb_.sc["alpha_hat"], h_prev, h_map, batch_sum=sb_.batch_sum,
+                         map_slot=sb_.maps[:, i % T_UC])
 
     e2e_step(0).synchronize()
     barrier()
@@ -371,25 +506,46 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
     e2e_val = world * B * H * W * e2e_steps / e2e_s / 1e6
-    sb = 4 if dtype == torch.float32 else 2
+    sb = sb_.sb
+    n_el = sb_.n_el
     h2d = n_el * ((M + 1) * sb + 4)
     d2h = n_el * 8
 
+    # ---- sub-records measured by every rank (collectives inside): the other scaling mode, the sampling loop
+    other = None
+    if world > 1 and not args.no_extras:
+        oB = B_total if scaling == "strong" else B_total // world
+        ob = StepBench(ops, args.workload, args.dtype, oB, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum)
+        o_ms, o_k = ob.quick(args.steps)
+        t = torch.tensor([o_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        other = {"scaling": "weak" if scaling == "strong" else "strong", "images_per_gpu": oB, "ms_per_step": t.item(),
+                 "value": world * oB * H * W / (t.item() * 1e-3) / 1e6, "unit": "Mpix/s", "kernel": ob.kernel, "kernel_ms": o_k}
+        del ob
+    loop = None
+    if args.with_loop and args.workload == "imagenet128_adm_b128_m5":
+        del host_step
+        torch.cuda.empty_cache()
+        loop = loop_record(args, "imagenet128_adm_loop", world, rank, local, dev, dist)
+
     if rank == 0:
         peak, peak_kind = peaks()
-        alg_step = algorithmic_bytes_per_element(M, sb) * n_el
+        alg_step = sb_.alg_bytes()
         # dominant kernel: the fused step moves exactly the step's algorithmic bytes; unfused: moments = M scores + eps in, u out
         alg_kernel = alg_step if fused else ((M + 1) * sb + 4) * n_el
         achieved = alg_kernel / (k_ms * 1e-3) / 1e9
+        dt_tag = {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype]
+        cfg = step_config(args.workload, B * world, world, sb_.batch_sum, dt_tag)
+        cfg.update({"images_per_gpu": B, "fused_single_launch": bool(fused),
+                    "parallelism": f"batch sharded x{world} ({B} images per GPU), no collective",
+                    "prev_out": f"ring of {StepBench.PREV_RING} buffers ({StepBench.PREV_RING * n_el * 4 / 1e6:.0f} MB): x_(t-1) is written to HBM, not absorbed by L2",
+                    "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
+                          if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)})
         line = {
             "metric": "uncertainty_step_throughput", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype], "data": "synthetic",
-            "config": {"workload": args.workload, "batch_per_gpu": B, "shape": [C, H, W], "M": M, "q": q,
-                       "chain": "F1c var(M+1) -> F2a quantile mask -> F5 posterior -> F3 DDIM (+F8 slot write)",
-                       "batch_sum": bool(args.batch_sum), "fused_single_launch": bool(fused), "parallelism": f"batch-sharded x{world}, no collective",
-                       "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
-                             if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)},
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": dt_tag, "data": "synthetic", "config": cfg,
+            "parity_checked": parity is not None, "parity": parity,
             "step_hbm_frac": alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
             "step_algorithmic_GBps": alg_step / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -404,8 +560,34 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks.summary(),
         }
+        if other is not None:
+            line["other_scaling"] = other
+        if loop is not None:
+            line["sampling_loop"] = loop
+        if world == 1 and not args.no_extras:
+            # the reference's eager torch expressions on this GPU: the bar a user of the reference compares against
+            eg_ms = sb_.time_eager_reference()
+            line["gpu_eager_baseline"] = {"value": B * H * W / (eg_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": eg_ms,
+                                          "what": "the reference's eager torch expressions (stack / var / quantile / blend / DDIM) on the "
+                                                  "same GPU and tensors, CUDA events, best of 5", "speedup_of_value": eg_ms / ms_per_step}
+            # the other BASELINE shapes and the autocast score dtype, same measurement in short form (parity-checked each)
+            subs = {}
+            for wl, dtn in ([(args.workload, "fp16")] if args.dtype == "fp32" else []) + [(w, "fp32") for w in WORKLOADS if w != args.workload]:
+                try:
+                    x = StepBench(ops, wl, dtn, WORKLOADS[wl][0], dev, 1234, batch_sum=args.batch_sum)
+                    x.warm(3)
+                    par = x.parity()
+                    s_ms, kk_ms = x.quick(args.steps)
+                    subs[f"{wl}:{dtn}"] = {"ms_per_step": s_ms, "kernel": x.kernel, "kernel_ms": kk_ms,
+                                           "value": x.B * x.H * x.W / (s_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                                           "roofline_frac": x.alg_bytes() / (kk_ms * 1e-3) / 1e9 / peak, "parity_checked": True,
+                                           "mask_agreement": par["mask_agreement"]}
+                    del x
+                except Exception as ex:   # a sub-record must not take the headline line down
+                    subs[f"{wl}:{dtn}"] = {"error": repr(ex)[:200]}
+            line["other_workloads"] = subs
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = time_cpu(args.workload, sample_images=32, budget_s=12.0)
+            line["cpu_baseline"] = time_cpu(args.workload, sample_images=B_total, budget_s=12.0)
         print(json.dumps(line), flush=True)
     del out
     if world > 1:
@@ -536,14 +718,14 @@ LOOPS = {
 }
 
 
-def run_loop(args):
+def loop_record(args, workload, world, rank, local, dev, dist):
     """BASELINE.json metric (iii): ImageNet-128 M=5 img/s over the FULL sampling loop of the README command
     (scripts/generate_dataset_score_uncertainty_imagenet.py: 50 DDIM steps, uncertainty window = the last 10, M=5 x num_zigzag=3
     perturbed forwards per window step, maps accumulated and copied to the host), through the drop-in
     `generate_samples_model_scheduler_class_conditioned_from_tensor` with the zigzag-centred scheduler, under torch.autocast as
     the reference runs it.  The score model is a random-init ADM-128-shaped feeder (tools/adm_feeder.py).  The batch of 128 is
-    SHARDED over the ranks (strong scaling, no collective) — the reference's mp.spawn slicing.  One step = one whole loop."""
-    import torch.distributed as dist
+    SHARDED over the ranks (strong scaling, no collective) — the reference's mp.spawn slicing.  One step = one whole loop.
+    Called by every rank (the process group, if any, is already up); returns the record on rank 0, None elsewhere."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import adm_feeder
     from diffusion_uncertainty_b200 import ops
@@ -551,16 +733,7 @@ def run_loop(args):
     from diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim_uncertainty_zigzag_centered import \
         DDIMSchedulerUncertaintyImagenetClassConditioned as Sched
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the uncertainty path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    factory, B_total, C, H, betas, skw, n_steps = LOOPS[args.workload]
+    factory, B_total, C, H, betas, skw, n_steps = LOOPS[workload]
     B = B_total // world
     model = getattr(adm_feeder, factory)().to(dev).eval()
     sched = Sched.from_config(dict(num_train_timesteps=1000, clip_sample=True, set_alpha_to_one=True, steps_offset=0,
@@ -616,28 +789,47 @@ def run_loop(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     n_fwd = n_steps + skw["num_steps_uc"] * skw["M"] * skw["num_zigzag"]
+    if rank != 0:
+        return None
+    ms_per_loop = ms / steps
+    unc = res["uncertainty"]
+    share = n_fwd * fwd_ms / ms_per_loop
+    return {
+        "metric": "imagenet%d_m5_sampling_loop_throughput" % H, "value": B_total / (ms_per_loop * 1e-3), "unit": "img/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_loop, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16 autocast (model) / f32 (uncertainty path)", "data": "synthetic",
+        "config": {"workload": workload, "global_batch": B_total, "batch_per_gpu": B, "generation_steps": n_steps,
+                   "start_step_uc": skw["after_step"], "num_steps_uc": skw["num_steps_uc"], "M": skw["M"],
+                   "num_zigzag": skw["num_zigzag"], "scheduler": "uncertainty_zigzag_centered",
+                   "model": "random-init ADM-%d-shaped feeder (tools/adm_feeder.py, %.1f M parameters)"
+                            % (H, sum(p.numel() for p in model.parameters()) / 1e6),
+                   "parallelism": f"batch-sharded x{world}, no collective", "step": "one full sampling loop of the batch"},
+        "model_forwards_per_loop": n_fwd, "model_forward_ms": fwd_ms,
+        "model_share_of_loop": share,
+        "non_model_ms_per_loop": ms_per_loop - n_fwd * fwd_ms,
+        "limiter": "the reference's PyTorch score model: %d forwards x %.1f ms at %d images per GPU = %.1f %% of the loop"
+                   % (n_fwd, fwd_ms, B, 100 * share),
+        "e2e": {"value": B_total / (ms_per_loop * 1e-3), "unit": "img/s", "h2d_bytes_per_step": X_T.numel() * 4 * world,
+                "d2h_bytes_per_step": (2 * unc.numel() * unc.element_size() + res["gen_images"].numel()) * world,
+                "note": "the loop itself is end to end: X_T comes from pinned host memory, maps / scores / uint8 images end in host memory"},
+        "gpu_launches": launches, "map_shape": list(unc.shape), "map_finite": bool(torch.isfinite(unc).all()),
+        "clocks": clocks.summary("the timed loops"),
+    }
+
+
+def run_loop(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device: the uncertainty path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = loop_record(args, args.workload, world, rank, local, dev, dist)
     if rank == 0:
-        ms_per_loop = ms / steps
-        unc = res["uncertainty"]
-        line = {
-            "metric": "imagenet%d_m5_sampling_loop_throughput" % H, "value": B_total / (ms_per_loop * 1e-3), "unit": "img/s",
-            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms_per_loop, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f16 autocast (model) / f32 (uncertainty path)", "data": "synthetic",
-            "config": {"workload": args.workload, "global_batch": B_total, "batch_per_gpu": B, "generation_steps": n_steps,
-                       "start_step_uc": skw["after_step"], "num_steps_uc": skw["num_steps_uc"], "M": skw["M"],
-                       "num_zigzag": skw["num_zigzag"], "scheduler": "uncertainty_zigzag_centered",
-                       "model": "random-init ADM-%d-shaped feeder (tools/adm_feeder.py, %.1f M parameters)"
-                                % (H, sum(p.numel() for p in model.parameters()) / 1e6),
-                       "parallelism": f"batch-sharded x{world}, no collective", "step": "one full sampling loop of the batch"},
-            "model_forwards_per_loop": n_fwd, "model_forward_ms": fwd_ms,
-            "model_share_of_loop": n_fwd * fwd_ms / ms_per_loop,
-            "non_model_ms_per_loop": ms_per_loop - n_fwd * fwd_ms,
-            "e2e": {"value": B_total / (ms_per_loop * 1e-3), "unit": "img/s", "h2d_bytes_per_step": X_T.numel() * 4 * world,
-                    "d2h_bytes_per_step": (2 * unc.numel() * unc.element_size() + res["gen_images"].numel()) * world,
-                    "note": "the loop itself is end to end: X_T comes from pinned host memory, maps / scores / uint8 images end in host memory"},
-            "gpu_launches": launches, "map_shape": list(unc.shape), "map_finite": bool(torch.isfinite(unc).all()),
-            "clocks": clocks.summary("the timed loops"),
-        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -660,6 +852,11 @@ def main():
     ap.add_argument("--shard-m", action="store_true", help="shard the M predictions over the ranks (SD-512 latent workload) instead of the batch")
     ap.add_argument("--seed-offset", type=int, default=0, help="added to the data seed 1234 + rank (to replay another rank's data on one GPU)")
     ap.add_argument("--eager", action="store_true", help="time K eager launches from Python instead of one CUDA graph of K steps")
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1: strong = the workload's batch split over the ranks (default, BASELINE configs[2]); weak = the whole batch on every GPU")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the timed configuration")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (other scaling mode, other workloads, fp16, eager-torch GPU baseline)")
+    ap.add_argument("--no-loop", dest="with_loop", action="store_false", help="skip the ImageNet-128 sampling-loop sub-record (img/s, ~1 min per loop at N=1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload in LOOPS:

@@ -47,6 +47,11 @@ __device__ __forceinline__ void stamp(const FusedKParams& kp, int slot) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     kp.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TL_SLOTS + slot] = t;
+    if (slot == 0) {   // last slot: the SM this CTA runs on (which CTAs share an SM explains the spread of the streaming times)
+      unsigned sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      kp.timeline[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TL_SLOTS + TL_SLOTS - 1] = sm;
+    }
   }
 }
 

@@ -321,8 +321,164 @@ def main_uvit():
          timestep=res["timestep"])
 
 
+class _StepRecorder:
+    """Wraps scheduler.step: keeps the last x_{t-1} (the pipelines return uint8 images only) and, with neutral=True, rewinds the
+    seeded noise generator after every step so that the scheduler's own draws (`best_noise`, every step) do not consume the
+    stream — what diffusers' DDIMScheduler, the scheduler the reference drives these pipelines with
+    (scripts/generate_images_with_uncertainty_threshold.py:202-203), does not draw at all."""
+
+    def __init__(self, sched, gen=None, neutral=False):
+        self.sched, self.gen, self.neutral, self.last = sched, gen, neutral, None
+        self.inner = sched.step
+        sched.step = self
+
+    def __call__(self, *a, **kw):
+        state = self.gen.get_state() if self.neutral else None
+        out = self.inner(*a, **kw)
+        if self.neutral:
+            self.gen.set_state(state)
+        self.last = out.prev_sample.detach().clone()
+        return out
+
+
+def _ref_plain_ddim(n_steps, **cfg):
+    """The reference's own DDIM arithmetic as a plain scheduler: the centred uncertainty scheduler with an EMPTY window."""
+    mod = __import__(SU + "scheduling_ddim_uncertainty_centered", fromlist=["x"])
+
+    class DDIMScheduler(mod.DDIMSchedulerUncertainty):
+        def set_timesteps(self, n, device=None):
+            self.config.after_step, self.config.num_steps_uc = 0, 1
+            super().set_timesteps(n, device)
+            self.timestep_after_step, self.timestep_end_step = -1, 10 ** 9
+
+    with quiet():
+        sched = DDIMScheduler.from_config(base_config(**cfg), unet=None, M=1)
+        sched.set_timesteps(n_steps)
+    return sched
+
+
+def main_pipelines():
+    """Fixtures of the pipeline classes and threshold-guided loops (VERDICT r1 missing 1-3): `python tests/golden/make_golden.py pipelines`."""
+    torch.manual_seed(0)
+    torch.set_num_threads(1)
+    cpu = torch.device("cpu")
+    from diffusion_uncertainty.pipeline_uncertainty import pipeline_sampler_class_conditional_uncertainty as pu
+    from diffusion_uncertainty.pipeline_uncertainty import \
+        pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution as pd
+    from diffusion_uncertainty.pipeline_uncertainty import pipeline_sampler_class_conditional_uncertainty_guided_second_order as so
+    from diffusion_uncertainty.pipeline_uncertainty import uncertainty_guidance as pug
+    import diffusion_uncertainty.generate_samples as gs
+    from diffusion_uncertainty.uvit.uvit_ae import UViTAE as RefUViTAE
+    from tests.toy_models import ToyUViTMixin
+
+    # ---- DiffusionClassConditionalWithUncertainty (:9-147) with the BASELINE scheduler, two batches
+    mod = __import__(SU + "scheduling_ddim_uncertainty_zigzag_centered", fromlist=["x"])
+    model = ToyADM(3, seed=50).eval()
+    g = torch.Generator().manual_seed(150)
+    x_T = torch.randn(6, 3, 16, 16, generator=g)
+    y = torch.randint(0, 10, (6,), generator=g)
+    with quiet():
+        sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(base_config(), unet=model, M=3, after_step=12,
+                                                                                 num_steps_uc=4, num_zigzag=2)
+        sched.set_timesteps(20)
+        pipe = pu.DiffusionClassConditionalWithUncertainty(model, sched, 16, cpu, 4, 0)
+        with seeded_noise(80):
+            res = pipe(X_T=x_T, y=y)
+    save("pipe_with_uncertainty", x_T=x_T, y=y, gen_images=res["gen_images"], uncertainty=res["uncertainty"], score=res["score"])
+
+    # ---- DiffusionClassConditionalGuidedPosteriorDistribution (:71-243), percentile and tensor thresholds.  Its __call__ passes
+    # three arguments to the four-argument module function (:159): the missing threshold_type is supplied here, nothing else changes.
+    orig = pd.calculate_threshold_map
+    pd.calculate_threshold_map = lambda thr, i, u, kind="higher": orig(thr, i, u, kind)
+    try:
+        for tag, thr in (("q", 0.9), ("t", None)):
+            model = ToyADM(3, seed=51).eval()
+            g = torch.Generator().manual_seed(151)
+            x_T = torch.randn(5, 3, 16, 16, generator=g)
+            y = torch.randint(0, 10, (5,), generator=g)
+            if thr is None:
+                thr = torch.rand(8, 3, 16, 16, generator=g) * 2e-3
+            sched = _ref_plain_ddim(8)
+            pipe = pd.DiffusionClassConditionalGuidedPosteriorDistribution(model, sched, thr, 16, cpu, 3, 0, M=4)
+            with seeded_noise(81) as gen, quiet():
+                rec = _StepRecorder(sched, gen, neutral=True)
+                finals = []
+                orig_cat = None
+                res = pipe(X_T=x_T, y=y, start_step=2, num_steps=3)
+            save(f"pipe_posterior_{tag}", x_T=x_T, y=y, gen_images=res["gen_images"], final_last_batch=rec.last,
+                 **({"threshold": thr} if torch.is_tensor(thr) else {"q": thr}))
+    finally:
+        pd.calculate_threshold_map = orig
+
+    # ---- DiffusionClassConditionalGuidedSecondOrder (:71-330)
+    model = ToyADM(3, seed=52).eval()
+    g = torch.Generator().manual_seed(152)
+    x_T = torch.randn(5, 3, 16, 16, generator=g)
+    y = torch.randint(0, 10, (5,), generator=g)
+    sched = _ref_plain_ddim(8)
+    pipe = so.DiffusionClassConditionalGuidedSecondOrder(model, sched, 0.85, 16, cpu, 3, 0, M=4, threshold_type="higher")
+    with seeded_noise(82) as gen, quiet():
+        rec = _StepRecorder(sched, gen, neutral=True)
+        res = pipe(X_T=x_T, y=y, start_step=2, num_steps=4)
+    save("pipe_second_order", x_T=x_T, y=y, gen_images=res["gen_images"], final_last_batch=rec.last, q=0.85)
+
+    # ---- PU/uncertainty_guidance.generate_samples_model_scheduler_class_conditioned_with_threshold (:12-125)
+    modc = __import__(SU + "scheduling_ddim_uncertainty_centered", fromlist=["x"])
+    model = ToyADMWithParameter(3, seed=53, scale=3.0).eval()   # scale 3: the guided update moves ~23 % of the pixels
+    g = torch.Generator().manual_seed(153)
+    x_T = torch.randn(5, 3, 16, 16, generator=g)
+    y = torch.randint(0, 10, (5,), generator=g)
+    thr = torch.rand(8, 3, 16, 16, generator=g) * 0.45
+    with quiet():
+        sched = modc.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(base_config(), unet=model, M=2, after_step=2, num_steps_uc=3)
+        sched.set_timesteps(8)
+        with seeded_noise(83):
+            rec = _StepRecorder(sched)
+            res = pug.generate_samples_model_scheduler_class_conditioned_with_threshold(
+                5, 3, 16, model, sched, 10, thr, device=cpu, x_T=x_T, y=y, start_step=2, num_steps=3)
+    save("loop_threshold_adm", x_T=x_T, y=y, threshold=thr, gen_images=res["gen_images"], final_last_batch=rec.last)
+
+    # ---- generate_samples_uvit_scheduler_class_conditioned_with_threshold (generate_samples.py:721-860; BASELINE config 4)
+    class ToyRefUViTAE(ToyUViTMixin, RefUViTAE):
+        def __init__(self, seed):
+            torch.nn.Module.__init__(self)
+            self.toy_init(seed)
+
+    model = ToyRefUViTAE(54).eval()
+    g = torch.Generator().manual_seed(154)
+    x_T = torch.randn(5, 4, 8, 8, generator=g)
+    y = torch.randint(0, 10, (5,), generator=g)
+    thr = torch.rand(8, 4, 8, 8, generator=g) * 0.02
+    with quiet():
+        sched = mod.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(
+            base_config(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, clip_sample=False, set_alpha_to_one=False,
+                        steps_offset=1), unet=model, M=2, after_step=2, num_steps_uc=3, num_zigzag=2)
+        sched.set_timesteps(8)
+        with seeded_noise(84):
+            rec = _StepRecorder(sched)
+            res = gs.generate_samples_uvit_scheduler_class_conditioned_with_threshold(
+                5, 3, 8, model, sched, 10, thr, device=cpu, x_T=x_T, y=y, start_step=2, num_steps=3)
+    save("loop_threshold_uvit", x_T=x_T, y=y, threshold=thr, gen_images=res["gen_images"], final_last_batch=rec.last)
+
+    # ---- generate_samples_model_scheduler_class_conditioned_with_percentile (generate_samples.py:861-983; legacy)
+    model = ToyADMWithParameter(3, seed=55, scale=3.0).eval()
+    g = torch.Generator().manual_seed(155)
+    x_T = torch.randn(4, 3, 16, 16, generator=g)
+    labels = torch.randint(0, 10, (4,), generator=g)
+    with quiet():
+        sched = modc.DDIMSchedulerUncertaintyImagenetClassConditioned.from_config(base_config(), unet=model, M=2, after_step=2, num_steps_uc=3)
+        sched.set_timesteps(8)
+        with seeded_noise(85):
+            rec = _StepRecorder(sched)
+            res = gs.generate_samples_model_scheduler_class_conditioned_with_percentile(
+                4, 4, 16, model, sched, labels, 0.9, device=cpu, x_T=x_T, start_step=2, num_steps=3)
+    save("loop_percentile_adm", x_T=x_T, y=labels, gen_images=res["gen_images"], final_last_batch=rec.last, q=0.9)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "uvit":
+    if len(sys.argv) > 1 and sys.argv[1] == "pipelines":
+        main_pipelines()
+    elif len(sys.argv) > 1 and sys.argv[1] == "uvit":
         main_uvit()
     elif len(sys.argv) > 1 and sys.argv[1] == "uncond":
         main_uncond()
