@@ -299,12 +299,23 @@ class StepBench:
         u_k = self.maps[:, 0]
         u, thr, mask, prev_ref = eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum)
         torch.cuda.synchronize()
-        # relative to max(u, 1e-3 mean(u)): a variance far below the typical one is the difference of nearly equal fp32 numbers,
-        # and no two summation orders agree on it to 1e-5 (torch.var's own error is of that size there)
-        rel_u = float(((u_k - u).abs() / u.abs().clamp_min(1e-3 * float(u.mean()))).max())
-        out = {"map_max_rel_err": rel_u, "map_max_rel_err_unfloored": float(((u_k - u).abs() / u.abs().clamp_min(1e-30)).max())}
+        # The bar for the map is the EXACT variance of the fp32 inputs (fp64 on the same device): within 1e-5 relative.  torch.var's
+        # own fp32 result is reported next to it: on pixels whose variance is far below the typical one it deviates from the exact
+        # value by more than that (its running mean is rounded at the magnitude of the samples, ~1e-7 absolute, against deviations
+        # of ~1e-3), so "equal to the reference's fp32 value to 1e-5" is not a property any implementation can have there; the
+        # kernel's shifted sums subtract nearby fp32 numbers exactly (Sterbenz) and stay at the 1e-6 level everywhere.
+        u64 = torch.var(torch.stack([s.double() for s in self.scores] + [self.eps.double()], dim=0), dim=0)
+        den = u64.abs().clamp_min(1e-300)
+        rel_u = float(((u_k.double() - u64).abs() / den).max())
+        rel_ref = float(((u.double() - u64).abs() / den).max())
+        out = {"map_max_rel_err_vs_exact": rel_u, "reference_fp32_max_rel_err_vs_exact": rel_ref,
+               "map_max_rel_diff_vs_reference_fp32": float(((u_k - u).abs() / u.abs().clamp_min(1e-30)).max())}
+        del u64, den
         if rel_u > 1e-5:
-            raise AssertionError(f"parity: map differs from torch.var by {rel_u:.3e} relative")
+            raise AssertionError(f"parity: map differs from the exact variance by {rel_u:.3e} relative")
+        # against the reference's fp32 value: within 1e-5 plus the reference's own deviation from the exact value
+        if out["map_max_rel_diff_vs_reference_fp32"] > 1e-5 + 1.01 * rel_ref:
+            raise AssertionError(f"parity: map differs from torch.var by {out['map_max_rel_diff_vs_reference_fp32']:.3e} relative")
         if self.fused:
             thr_k = self.plan.res["thr"]
             thr_c = torch.quantile(u_k.flatten(1).cpu(), self.q, dim=1)    # (torch's CUDA lerp contracts to an FMA: compare on the host)

@@ -233,7 +233,9 @@ __device__ __forceinline__ void accumulate_scores(const void* const* scores, int
 // Same contract as accumulate_scores with M known at compile time: no predication, every load of a batch (<= 8 score
 // vectors + the centre) is issued before the first use.
 // HINT: the score loads carry the L2 eviction policy `pol` (see ldg_stream_128_pol)
-template <typename T, int MT, bool HINT = false, typename V = Vec16<T>>
+// SKIP0: the caller guarantees shift_first (the shift IS sample 0): its deviation is x0 - x0, i.e. +0 — or NaN for a non-finite
+// x0, in which case every other deviation is NaN or infinite as well and the result is NaN either way — so the term is dropped.
+template <typename T, int MT, bool HINT = false, typename V = Vec16<T>, bool SKIP0 = false>
 __device__ __forceinline__ void accumulate_scores_ct(const void* const* scores, int64_t row_off, uint32_t byte_off, const uint4& raw_c,
                                                      int centre_mode, bool c_ready, bool shift_first,
                                                      float (&c)[V::VEC], float (&k)[V::VEC],
@@ -269,11 +271,15 @@ __device__ __forceinline__ void accumulate_scores_ct(const void* const* scores, 
     }
 #pragma unroll
     for (int j = 0; j < BATCH; ++j) {
-      if (m0 + j < MT) {
+      if (m0 + j < MT && !(SKIP0 && m0 + j == 0)) {
         float x[VEC];
         V::unpack(raw[j], x);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) { const float d = x[e] - k[e]; s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+        for (int e = 0; e < VEC; ++e) {
+          const float d = x[e] - k[e];
+          if (SKIP0 && m0 + j == 1) { s1[e] = d; s2[e] = d * d; }     // (0 + d and fma(d, d, 0): the same values)
+          else { s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+        }
       }
     }
   }
@@ -287,6 +293,15 @@ __device__ __forceinline__ void accumulate_scores_ct(const void* const* scores, 
 __device__ __forceinline__ float m2_from_sums(float s1, float s2, float inv_cnt) {
   const float m2 = fmaf(-s1 * inv_cnt, s1, s2);
   return (m2 < 0.0f) ? 0.0f : m2;
+}
+// The map value of the fused kernels from the shifted sums, never -0.0 (its bit pattern must order like its value):
+// centre_mode 1: s2 / count; else max(m2, +0) / (count - 1) with NaN kept (max.NaN) — the same values as
+// fmaf(m2_from_sums(..), inv_cm1, 0.0f), two instructions shorter per element.
+__device__ __forceinline__ float map_value(int centre_mode, float s1, float s2, float inv_cnt, float inv_cm1) {
+  if (centre_mode == 1) return fmaf(s2, inv_cnt, 0.0f);
+  float m2 = fmaf(-s1 * inv_cnt, s1, s2);
+  asm("max.NaN.f32 %0, %0, 0f00000000;" : "+f"(m2));
+  return m2 * inv_cm1;
 }
 
 // 4 consecutive elements starting at element index idx (idx % 4 == 0, pointer suitably aligned)

@@ -61,7 +61,10 @@ __device__ __forceinline__ void guided_elem(const du_ddim_coeffs& dc, float post
 // NARROW: 16-bit scores are read as 8-byte vectors (4 elements per thread and trip, like fp32) instead of 16-byte ones: the
 // loop then has the register budget and the trip count of the fp32 instance (8 elements per thread spilled and left only 6
 // trips, below the point where the single pass pays).
-template <typename T, int MT, int THREADS, int MINB, bool OUTS, bool NARROW>
+// SPEC: 1 = the reference's percentile-guided step as its callers run it — variance over the M scores AND the centre
+// (DU_MOM_VAR_WITH_CENTER), posterior sum source S given: the two facts are compile-time constants of the streaming loop (no
+// per-trip selects on the moments mode, no S-or-eps select); 0 = any mode, S optional.
+template <typename T, int MT, int THREADS, int MINB, bool OUTS, bool NARROW, int SPEC>
 __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_constant__ PredKParams pk) {
   using FV = typename std::conditional<NARROW, Vec8<T>, Vec16<T>>::type;
   constexpr int VEC = FV::VEC;
@@ -69,8 +72,10 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   const FusedKParams& kp = pk.k;
   const du_fused_params& p = kp.p;
   cg::cluster_group cluster = cg::this_cluster();
-  const unsigned csize = cluster.num_blocks();
-  const unsigned crank = (csize > 1) ? cluster.block_rank() : 0u;
+  // the grid is (cluster size, B) with cluster dimensions (cluster size, 1, 1): the rank in the cluster IS blockIdx.x.  Taking it
+  // from there (instead of %cluster_ctarank, which arrives in a vector register) keeps every row base address CTA-uniform.
+  const unsigned csize = gridDim.x;
+  const unsigned crank = blockIdx.x;
   const int64_t b = blockIdx.y;
   const int64_t L = kp.L;
   const int64_t base = (int64_t)crank * L;
@@ -88,10 +93,11 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   uint32_t* hp = work;
   // candidates, structure of arrays: key, element index within the slice, and the inputs of the update (eps, sample, S) so
   // that the patch pass touches no global memory for its reads
-  uint32_t* cand_key = misc + MISC_WORDS;
-  uint32_t* cand_idx = cand_key + pk.cand_max;
-  float* cand_e = reinterpret_cast<float*>(cand_idx + pk.cand_max);
-  float* cand_s = cand_e + pk.cand_max;
+  // candidates: one 16-byte record {key, element index, eps bits, sample bits} each — a single predicated st.shared.v4 in the
+  // streaming loop, and the patch pass touches no global memory for its reads
+  uint4* cand = reinterpret_cast<uint4*>(misc + MISC_WORDS);
+  const uint32_t cand_addr = (uint32_t)__cvta_generic_to_shared(cand);
+  const uint32_t cand_cnt_addr = (uint32_t)__cvta_generic_to_shared(&misc[44]);
 
   for (int j = tid; j < H0_WORDS + PRED_WORK_WORDS; j += THREADS) h0[j] = 0;
   if (tid < MISC_WORDS) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
@@ -102,13 +108,16 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   const bool higher = p.higher != 0;
   const float post_M = p.post_M, inv_ah = p.inv_alpha_hat, inv_sa = kp.inv_sqrt_alpha_t;
   const int mode = p.moments_mode;
-  const int centre_mode = (mode == DU_MOM_CENTERED) ? 1 : ((mode == DU_MOM_VAR_WITH_CENTER) ? 2 : 0);
+  const int centre_mode = SPEC ? 2 : ((mode == DU_MOM_CENTERED) ? 1 : ((mode == DU_MOM_VAR_WITH_CENTER) ? 2 : 0));
   const int64_t srow = b * p.score_stride + base, erow = b * p.eps_stride + base, xrow = b * p.sample_stride + base;
   const T* eps_row = reinterpret_cast<const T*>(p.eps) + erow;
   const float* xs = reinterpret_cast<const float*>(p.sample) + xrow;
   float* urow = p.unc_out + b * p.unc_stride + base;
   float* prow = reinterpret_cast<float*>(p.prev_out) + b * p.prev_stride + base;
-  const float* Srow = p.S ? (p.S + (p.S_broadcast ? 0 : b * p.S_stride) + base) : nullptr;
+  const float* Srow = (SPEC || p.S) ? (p.S + (p.S_broadcast ? 0 : b * p.S_stride) + base) : nullptr;
+  const bool has_S = SPEC ? true : (Srow != nullptr);
+  // mask by band as ONE unsigned compare: `higher`: key >= UB  <=>  key - UB < 2^32 - UB;  `lower`: key < LB  <=>  key - 0 < LB
+  uint32_t one_lo = 0, one_w = 0;
   const int ngroups = (int)(L / VEC);
   const int trips = (int)pk.trips;
   uint32_t nan_seen = 0;
@@ -129,18 +138,18 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       if (!pilot_only) {
 #pragma unroll
         for (int h = 0; h < VEC / 4; ++h) raw_s[h] = ldg_stream_128_pol(xs + g_elems + 4 * h, pol);
-        if (Srow) {
+        if (has_S) {
 #pragma unroll
           for (int h = 0; h < VEC / 4; ++h) raw_S[h] = ld_coherent_f4(Srow + g_elems + 4 * h);
         }
       }
       if (from_scores) {
         float c[VEC], k[VEC], s1[VEC], s2[VEC];
-        if constexpr (MT > 0) accumulate_scores_ct<T, MT, true, FV>(p.scores, srow, byte_off, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2, pol);
+        if constexpr (MT > 1 && SPEC == 1) accumulate_scores_ct<T, MT, true, FV, true>(p.scores, srow, byte_off, raw_e, 2, false, true, c, k, s1, s2, pol);
+        else if constexpr (MT > 0) accumulate_scores_ct<T, MT, true, FV>(p.scores, srow, byte_off, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2, pol);
         else accumulate_scores<T>(p.scores, p.M, srow + g_elems, raw_e, centre_mode, false, centre_mode != 1, c, k, s1, s2);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e)
-          u[e] = (centre_mode == 1) ? fmaf(s2[e], kp.inv_cnt, 0.0f) : fmaf(m2_from_sums(s1[e], s2[e], kp.inv_cnt), kp.inv_cm1, 0.0f);
+        for (int e = 0; e < VEC; ++e) u[e] = map_value(centre_mode, s1[e], s2[e], kp.inv_cnt, kp.inv_cm1);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
           nan_seen |= (u[e] != u[e]);
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
         for (int h = 0; h < VEC / 4; ++h) {
           s[4 * h] = __uint_as_float(raw_s[h].x); s[4 * h + 1] = __uint_as_float(raw_s[h].y);
           s[4 * h + 2] = __uint_as_float(raw_s[h].z); s[4 * h + 3] = __uint_as_float(raw_s[h].w);
-          if (Srow) { Sv[4 * h] = raw_S[h].x; Sv[4 * h + 1] = raw_S[h].y; Sv[4 * h + 2] = raw_S[h].z; Sv[4 * h + 3] = raw_S[h].w; }
+          if (has_S) { Sv[4 * h] = raw_S[h].x; Sv[4 * h + 1] = raw_S[h].y; Sv[4 * h + 2] = raw_S[h].z; Sv[4 * h + 3] = raw_S[h].w; }
           else { Sv[4 * h] = e0[4 * h]; Sv[4 * h + 1] = e0[4 * h + 1]; Sv[4 * h + 2] = e0[4 * h + 2]; Sv[4 * h + 3] = e0[4 * h + 3]; }
         }
       }
@@ -178,32 +187,29 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
 #pragma unroll
       for (int e = 0; e < VEC; ++e) inband |= (((__float_as_uint(u[e]) - LB) < (UB - LB)) ? 1u : 0u) << e;
     }
-    if (inband != 0u) {
-      // The streaming loop is close to issue-bound, so this stays short: one shared-memory atomic per LANE that has
-      // candidates (about a quarter of the lanes; same-address conflicts are resolved by the atomic unit), one overflow
-      // test per group, predicated stores.  The order of the list does not matter.
+    {
+      // The streaming loop is issue-bound, so the append has no branches: one predicated shared-memory atomic per lane that has
+      // candidates (about a quarter of the lanes), then one predicated 16-byte store per candidate.  Order does not matter.
       const uint32_t cnt = __popc(inband);
-      uint32_t slot = atomicAdd(&misc[44], cnt);
-      if (slot + cnt <= pk.cand_max) {
+      uint32_t slot = 0;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], %3;\n\t}"
+                   : "+r"(slot) : "r"(cand_cnt_addr), "r"(inband), "r"(cnt) : "memory");
+      const bool room = slot + cnt <= pk.cand_max;
+      if (inband != 0u && !room) misc[45] = 1u;
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          if (inband & (1u << e)) {
-            cand_key[slot] = __float_as_uint(u[e]); cand_idx[slot] = g_elems + e;
-            cand_e[slot] = e0[e]; cand_s[slot] = s[e];
-            ++slot;
-          }
-        }
-      } else {
-        misc[45] = 1u;
+      for (int e = 0; e < VEC; ++e) {
+        const uint32_t take = (room && (inband & (1u << e))) ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
+                     ::"r"(cand_addr + slot * 16u), "r"(__float_as_uint(u[e])), "r"(g_elems + e), "r"(__float_as_uint(e0[e])),
+                       "r"(__float_as_uint(s[e])), "r"(take) : "memory");
+        slot += take;
       }
     }
     if (valid) {
       float pv[VEC], x0v[VEC], eg[VEC], mk[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        const uint32_t key = __float_as_uint(u[e]);
-        const bool one = higher ? (key >= UB) : (key < LB);
-        mk[e] = one ? 1.0f : 0.0f;
+        mk[e] = ((__float_as_uint(u[e]) - one_lo) < one_w) ? 1.0f : 0.0f;
         guided_elem(dc, post_M, inv_ah, inv_sa, u[e], e0[e], s[e], Sv[e], mk[e], eg[e], x0v[e], pv[e]);
       }
 #pragma unroll
@@ -249,6 +255,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   __syncthreads();
   LB = lb_bin << LOW;
   UB = ub_bin << LOW;   // 4096 << 19 = 2^31: above every finite key and every NaN pattern with sign 0
+  one_lo = higher ? UB : 0u;
+  one_w = higher ? (0u - UB) : LB;   // (UB = 0 cannot occur: ub_bin >= 1)
   stamp(kp, 1);
 
   // ---------------------------------------------------------------- stream: every other trip, then the pilot replayed
@@ -296,7 +304,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
     const uint32_t want = d0 << LOW;
     const uint32_t ncand = misc[44];
     for (uint32_t i = tid; i < ncand; i += THREADS) {
-      const uint32_t key = cand_key[i];
+      const uint32_t key = cand[i].x;
       if ((key >> LOW) == d0) {
         list[atomicAdd(&misc[6], 1u)] = key;
         atomicAdd(&h1[(key >> H2_BITS) & (H1_BINS - 1)], 1u);
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       // the successor lives in a higher level-0 bin: smallest candidate key above key_lo, cluster-wide ...
       if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
       uint32_t best = 0xffffffffu;
-      for (uint32_t i = tid; i < ncand; i += THREADS) { const uint32_t key = cand_key[i]; if (key > key_lo) best = min(best, key); }
+      for (uint32_t i = tid; i < ncand; i += THREADS) { const uint32_t key = cand[i].x; if (key > key_lo) best = min(best, key); }
       best = __reduce_min_sync(0xffffffffu, best);
       if (lane == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
       sync_all();
@@ -342,13 +350,14 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
     if (!redo) {
       // ---- patch the candidates with the exact compare (all inputs come from the shared-memory stash)
       for (uint32_t i = tid; i < ncand; i += THREADS) {
-        const float u = __uint_as_float(cand_key[i]);
-        const int64_t o = cand_idx[i];
+        const uint4 rec = cand[i];
+        const float u = __uint_as_float(rec.x);
+        const int64_t o = rec.y;
         const float mk = (higher ? (u > thr) : (u < thr)) ? 1.0f : 0.0f;
         float eg, x0, pv;
-        const float e0 = cand_e[i];
-        const float Sv = Srow ? ld_coherent_f1(Srow + o) : e0;   // the S row is shared by every image of the batch: L2 / L1 resident
-        guided_elem(dc, post_M, inv_ah, inv_sa, u, e0, cand_s[i], Sv, mk, eg, x0, pv);
+        const float e0 = __uint_as_float(rec.z);
+        const float Sv = has_S ? ld_coherent_f1(Srow + o) : e0;   // the S row is shared by every image of the batch: L2 / L1 resident
+        guided_elem(dc, post_M, inv_ah, inv_sa, u, e0, __uint_as_float(rec.w), Sv, mk, eg, x0, pv);
         prow[o] = pv;
         if constexpr (OUTS) {
           if (p.x0_out) reinterpret_cast<float*>(p.x0_out)[b * p.x0_stride + base + o] = x0;
@@ -370,9 +379,9 @@ static constexpr size_t kPredFixedBytes = (size_t)(H0_WORDS + PRED_WORK_WORDS + 
 template <typename T, int MT>
 constexpr bool pred_narrow() { return sizeof(T) == 2 && MT > 0; }
 
-template <typename T, int MT, int THREADS, int MINB, bool OUTS>
-static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t smem, cudaStream_t st) {
-  auto kern = fused_pred_kernel<T, MT, THREADS, MINB, OUTS, pred_narrow<T, MT>()>;
+template <typename T, int MT, int THREADS, int MINB, bool OUTS, int SPEC>
+static int launch_pred_ts(const PredKParams& pk, const FusedPlan& plan, size_t smem, cudaStream_t st) {
+  auto kern = fused_pred_kernel<T, MT, THREADS, MINB, OUTS, pred_narrow<T, MT>(), SPEC>;
   static size_t smem_set[64] = {0};
   int dev = 0;
   DU_CUDA(cudaGetDevice(&dev));
@@ -404,6 +413,17 @@ static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t sm
   return 1;
 }
 
+template <typename T, int MT, int THREADS, int MINB, bool OUTS>
+static int launch_pred_t(const PredKParams& pk, const FusedPlan& plan, size_t smem, cudaStream_t st) {
+  // the specialised streaming loop for the step the reference's callers run (the bench / pipeline configuration); the optional
+  // outputs are a test / debugging feature and keep the generic loop
+  if constexpr (!OUTS && MT > 0) {
+    if (pk.k.p.moments_mode == DU_MOM_VAR_WITH_CENTER && pk.k.p.S != nullptr)
+      return launch_pred_ts<T, MT, THREADS, MINB, OUTS, 1>(pk, plan, smem, st);
+  }
+  return launch_pred_ts<T, MT, THREADS, MINB, OUTS, 0>(pk, plan, smem, st);
+}
+
 template <typename T, int MT, bool OUTS>
 static int launch_pred_m(const PredKParams& pk, const FusedPlan& plan, int threads, size_t smem, cudaStream_t st) {
 #ifdef DU_PRED_DEV   // development builds: one thread configuration (csrc/build.sh -DDU_PRED_DEV), a third of the compile time
@@ -411,8 +431,8 @@ static int launch_pred_m(const PredKParams& pk, const FusedPlan& plan, int threa
   return launch_pred_t<T, MT, 512, 2, OUTS>(pk, plan, smem, st);
 #else
   switch (threads) {
+#ifdef DU_PRED_TUNING   // 1024-thread and 384 / 768-thread CTAs (80 registers): measured slower, kept for sweeps only (csrc/build.sh -DDU_PRED_TUNING)
     case 1024: return launch_pred_t<T, MT, 1024, 1, OUTS>(pk, plan, smem, st);
-#ifdef DU_PRED_TUNING   // 384 / 768-thread CTAs (80 registers): measured slower, kept for sweeps only (csrc/build.sh -DDU_PRED_TUNING)
     case 768: return launch_pred_t<T, MT, 768, 1, OUTS>(pk, plan, smem, st);
     case 384: return launch_pred_t<T, MT, 384, 2, OUTS>(pk, plan, smem, st);
 #endif
