@@ -7,31 +7,29 @@
 namespace du {
 
 // =====================================================================================================================
-// The PREDICTIVE single-pass step.  The three-phase kernel above leaves HBM idle while an image's threshold is selected
-// and runs the update as a second, issue-bound pass; both sit on the critical path of every CTA (they all stream in
-// lock-step).  Here the update is folded into the streaming pass:
+// The PREDICTIVE single-pass step.  The three-phase kernel leaves HBM idle while an image's threshold is selected and runs the
+// update as a second pass; both sit on the critical path of every CTA (they all stream in lock-step).  Here the update is
+// folded into the streaming pass:
 //   pilot     trip 0 of every thread covers a systematic 1/trips row sample of the slice (a warp owns `trips` consecutive
-//             rows and reads one per trip).  Its map values are histogrammed; after ONE cluster barrier every CTA locates
-//             pilot ranks rank_p -/+ Delta (Delta = a few standard deviations of the sample quantile) in the summed pilot
-//             histograms: the level-0 bins [LB, UB) that will contain the image's two order statistics.
-//   stream    every other trip loads the M scores, eps, the sample (and S), computes the map value, histograms it, and
-//             applies mask -> posterior -> DDIM immediately: below the band the mask is certainly 0 (1 for `lower`), above
-//             it certainly 1 (0).  The few per cent inside the band are appended to a candidate list (key, element) and
-//             written provisionally.  The pilot trip is then replayed from L2 through the same code.
-//   finish    exact select: level-0 bin of rank lo from the FULL histogram; it must lie inside the band (verified, not
-//             assumed), the keys of that bin come from the candidate list, list_select() finishes.  The candidates are
-//             then patched with the exact compare.
-// If the verification fails (band missed, NaN, ties overflowing the lists) the image falls back to the exact select over
-// the map in L2 and a full update pass: always the exact result, only slower.
+//             rows and reads one per trip).  Its map values are histogrammed (4096 level-0 bins); after ONE cluster barrier every
+//             CTA locates pilot ranks rank_p -/+ Delta (Delta = a few standard deviations of the sample quantile) in the summed
+//             pilot histograms: the key range [LB, UB) that will contain the image's two order statistics.
+//   stream    every other trip loads the M scores, eps, the sample (and S), computes the map value and applies mask ->
+//             posterior -> DDIM immediately: below the band the mask is certainly 0 (1 for `lower`), above it certainly 1 (0).
+//             Keys below the band are only COUNTED (a register); the few per cent inside it are histogrammed at FINE resolution
+//             (1024 bins across the band), appended to a candidate list (key, element, eps, sample) and written provisionally.
+//             The pilot trip is then replayed from L2 through the same code.
+//   finish    rank lo - (keys below the band) must fall inside the band (verified, never assumed); ONE search over the summed
+//             fine histograms gives the bin of ~3 keys that holds it, every CTA picks those keys out of the cluster's candidate
+//             lists (DSMEM reads, no copy) and warp 0 ranks them.  The candidates are then patched with the exact compare.
+//             Two cluster barriers in all (pilot, end of stream) plus one split arrive / wait before exit.
+// If the verification fails (band missed, NaN, candidate / tie overflow) the image falls back to the exact select over the map
+// in L2 (level-0 histogram rebuilt there) and a full update pass: always the exact result, only slower.
 // =====================================================================================================================
-// Capacity of the key list of the selected level-0 bin.  That bin holds n * (probability mass of one bin) keys — about 920 of
-// the 49152 of an ImageNet-128 image at q = 0.9 (measured: 915..1025 over 1024 images).  With LIST_CAP = 1024 one image in a
-// thousand took the general path and held the whole launch back by 20 us (seen as one slow rank at N = 4); 2048 entries leave
-// more than 30 standard deviations.  The three-phase kernel keeps 1024 (its shared memory is sized by the map).
-constexpr int PRED_LIST_CAP = 2048;
-constexpr int PRED_WORK_WORDS = PRED_LIST_CAP + H1_BINS;
-static_assert(PRED_LIST_CAP <= H0_WORDS, "list_select parks the tiny list in the level-0 histogram's words");
-static_assert(PRED_WORK_WORDS >= WORK_WORDS && PRED_WORK_WORDS >= H0_WORDS, "the general path and the pilot histogram reuse the work area");
+constexpr int FINE_BINS = H1_BINS;          // 1024 bins across the band (the search reuses locate_rank<H1_BINS>)
+constexpr int TINY_CAP = H0_WORDS;          // keys of the selected fine bin, parked in the (then free) pilot-histogram words
+constexpr int PRED_WORK_WORDS = (FINE_BINS > WORK_WORDS) ? FINE_BINS : WORK_WORDS;   // fine histogram; the fallback's work area
+constexpr int ROWCTR_WORDS = 32;            // one claim counter per warp (<= 32 warps per CTA)
 
 struct PredKParams {
   FusedKParams k;
@@ -39,11 +37,11 @@ struct PredKParams {
   uint32_t r_lo, r_hi;  // pilot ranks bounding the band (cluster-wide pilot histogram)
   uint32_t open_low, open_high;  // band is open at that end (rank window touched the ends of the pilot sample)
   uint32_t cand_max;    // capacity of the candidate list (entries)
-  uint32_t prefetch_rows;  // rows per warp pulled into L2 while the pilot runs
+  uint32_t steal;       // warps that ran out of rows claim rows of the other blocks of the cluster (DU_FUSED_STEAL=0 disables)
   uint64_t pol_stream;     // L2 eviction policy of the once-read streams (scores, sample, eps on its last read)
 };
 
-// misc words used only here: [44] candidate count, [45] list overflow, [46] LB bin, [47] UB bin
+// misc words used only here: [44] candidate count, [45] list overflow, [46] keys below the band
 __device__ __forceinline__ void guided_elem(const du_ddim_coeffs& dc, float post_M, float inv_ah, float inv_sa, float u, float e0,
                                             float s, float S, float mk, float& eg, float& x0, float& pv) {
   // same expressions as guided_update_slice<FAST>
@@ -56,14 +54,114 @@ __device__ __forceinline__ void guided_elem(const du_ddim_coeffs& dc, float post
   pv = fmaf(dc.sqrt_alpha_prev, x0, dc.dir_coef * eg);
 }
 
+// The exact select inside the band.  Precondition: every CTA of the cluster has its fine histogram `hb`, its candidate records
+// (count in misc[44]) and its flags complete, and a cluster barrier has been passed.  `r` = rank of key_lo among the in-band keys
+// of the cluster.  Every CTA locates the fine bin in the summed histograms, copies the keys of that bin out of the cluster's
+// candidate lists (DSMEM reads) and warp 0 ranks them.  Results: misc[41] = key_lo, misc[43] = key_hi (0xffffffff: the successor
+// is not inside the band); returns false (cluster-uniform) when the bin holds more keys than `tiny` takes (heavy ties).
+// Leaves ONE cluster-barrier arrival pending (issued after the last DSMEM read).
+template <int THREADS>
+__device__ __forceinline__ bool band_select(cg::cluster_group& cluster, unsigned csize, unsigned crank, const FusedKParams& kp,
+                                            uint32_t* tiny, const uint4* cand, uint32_t* hb, uint32_t* misc, uint32_t LB, uint32_t sh,
+                                            uint32_t r) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  locate_rank<FINE_BINS, THREADS, true, false>(cluster, csize, hb, r, misc);
+  stamp(kp, 7);
+  const uint32_t f1 = misc[0], below1 = misc[1], cnt1 = misc[2], next1 = misc[5];
+  const uint32_t k2 = r - below1;                        // rank of key_lo among the cnt1 keys of the fine bin
+  const bool need_next = kp.hi > kp.lo;                  // the upper statistic is the next key in sorted order
+  const bool fits = cnt1 <= (uint32_t)TINY_CAP;
+  if (fits) {
+    const bool want_next_bin = need_next && (k2 + 1 >= cnt1) && next1 < (uint32_t)FINE_BINS;
+    uint32_t best = 0xffffffffu;
+    for (unsigned i = 0; i < csize; ++i) {
+      const unsigned rr = (crank + i) % csize;
+      const uint32_t* pm = (csize > 1) ? cluster.map_shared_rank(misc, rr) : misc;
+      const uint4* pc = (csize > 1) ? cluster.map_shared_rank(const_cast<uint4*>(cand), rr) : cand;
+      const uint32_t cr = pm[44];
+      // keys first (4 independent shared-memory / DSMEM loads in flight per thread), then the filter: the loop is latency-bound
+      for (uint32_t j0 = tid; j0 < cr; j0 += 4 * THREADS) {
+        uint32_t key[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t j = j0 + q4 * THREADS;
+          key[q4] = (j < cr) ? pc[j].x : 0xffffffffu;     // (0xffffffff - LB) >> sh is beyond every fine bin
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t fb = (key[q4] - LB) >> sh;
+          if (fb == f1) tiny[atomicAdd(&misc[40], 1u)] = key[q4];
+          else if (want_next_bin && fb == next1) best = min(best, key[q4]);
+        }
+      }
+    }
+    if (want_next_bin) {
+      best = __reduce_min_sync(0xffffffffu, best);
+      if (lane == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
+    }
+  }
+  if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");  // peers' lists, histograms and flags are read
+  stamp(kp, 8);
+  __syncthreads();
+  if (fits && tid < 32) {
+    // warp 0: k2-th smallest (and its successor) of the cnt1 keys in `tiny` — normally a handful: one key per lane, rank = number
+    // of smaller keys (ties broken by position) from m independent shuffle rounds
+    const uint32_t m = misc[40];   // == cnt1
+    const uint32_t bin_lo = LB + (f1 << sh);
+    uint32_t key_lo, key_hi;
+    if (m <= 32u) {
+      const uint32_t mine = (lane < (int)m) ? tiny[lane] : 0xffffffffu;
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t kj = __shfl_sync(0xffffffffu, mine, (int)j);
+        rank += (kj < mine || (kj == mine && j < (uint32_t)lane)) ? 1u : 0u;
+      }
+      const uint32_t is_lo = __ballot_sync(0xffffffffu, lane < (int)m && rank == k2);
+      const uint32_t is_hi = __ballot_sync(0xffffffffu, lane < (int)m && rank == k2 + 1u);
+      key_lo = __shfl_sync(0xffffffffu, mine, __ffs((int)is_lo) - 1);
+      key_hi = key_lo;
+      if (need_next) key_hi = is_hi ? __shfl_sync(0xffffffffu, mine, __ffs((int)is_hi) - 1) : misc[4];
+    } else {
+      // many keys in one fine bin (ties): bitwise search over the `sh` low bits of key - bin_lo
+      uint32_t ans = 0;
+#pragma unroll 1
+      for (int bit = (int)sh - 1; bit >= 0; --bit) {
+        const uint32_t trial = ans | (1u << bit);
+        uint32_t c = 0;
+        for (uint32_t j = lane; j < m; j += 32) c += ((tiny[j] - bin_lo) < trial);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c <= k2) ans |= (1u << bit);
+      }
+      key_lo = bin_lo + ans;
+      key_hi = key_lo;
+      if (need_next) {
+        // successor: a tie, else the smallest larger key of the bin, else the smallest key of the next non-empty fine bin
+        uint32_t le = 0, above = 0xffffffffu;
+        for (uint32_t j = lane; j < m; j += 32) {
+          const uint32_t key = tiny[j];
+          le += (key <= key_lo);
+          if (key > key_lo) above = min(above, key);
+        }
+        le = __reduce_add_sync(0xffffffffu, le);
+        above = __reduce_min_sync(0xffffffffu, above);
+        if (k2 + 1 < le) key_hi = key_lo;
+        else if (above != 0xffffffffu) key_hi = above;
+        else key_hi = misc[4];   // 0xffffffff: the successor lies above the band
+      }
+    }
+    if (lane == 0) { misc[41] = key_lo; misc[43] = key_hi; }
+  }
+  stamp(kp, 10);
+  __syncthreads();
+  return fits;
+}
+
 // OUTS: some of the optional outputs (x0, guided eps, mask) are requested; the common launch writes x_{t-1} only and keeps
-// none of those values alive in the (register-bound) streaming loop.
+// none of those values alive in the streaming loop.
 // NARROW: 16-bit scores are read as 8-byte vectors (4 elements per thread and trip, like fp32) instead of 16-byte ones: the
-// loop then has the register budget and the trip count of the fp32 instance (8 elements per thread spilled and left only 6
-// trips, below the point where the single pass pays).
+// loop then has the register budget and the trip count of the fp32 instance.
 // SPEC: 1 = the reference's percentile-guided step as its callers run it — variance over the M scores AND the centre
-// (DU_MOM_VAR_WITH_CENTER), posterior sum source S given: the two facts are compile-time constants of the streaming loop (no
-// per-trip selects on the moments mode, no S-or-eps select); 0 = any mode, S optional.
+// (DU_MOM_VAR_WITH_CENTER), posterior sum source S given: both are compile-time constants of the streaming loop; 0 = any mode.
 template <typename T, int MT, int THREADS, int MINB, bool OUTS, bool NARROW, int SPEC>
 __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_constant__ PredKParams pk) {
   using FV = typename std::conditional<NARROW, Vec8<T>, Vec16<T>>::type;
@@ -84,23 +182,25 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   auto peer = [&](uint32_t* ptr, unsigned r) -> uint32_t* { return (csize > 1) ? cluster.map_shared_rank(ptr, r) : ptr; };
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* h0 = reinterpret_cast<uint32_t*>(smem_raw);   // full level-0 histogram (packed 16-bit)
-  uint32_t* work = h0 + H0_WORDS;                         // key list + level-1 histogram (or the fallback's levels 1 / 2)
+  // [hp: level-0 histogram of the pilot sample, packed 16-bit; peers read it through DSMEM during their band search only; later the
+  //  tiny key list of the finish (or the level-0 histogram of the fallback)] [work: the fine band histogram (or the fallback's
+  //  levels 1 / 2)] [misc] [candidate records]
+  uint32_t* hp = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* work = hp + H0_WORDS;
+  uint32_t* hb = work;
   uint32_t* misc = work + PRED_WORK_WORDS;
-  // The pilot histogram (packed 16-bit) shares the work area: peers read it through DSMEM only during their band search,
-  // which every CTA acknowledges with a cluster-barrier arrival; the matching wait sits after the streaming pass, and only
-  // then is the area cleared for the select.
-  uint32_t* hp = work;
-  // candidates, structure of arrays: key, element index within the slice, and the inputs of the update (eps, sample, S) so
-  // that the patch pass touches no global memory for its reads
   // candidates: one 16-byte record {key, element index, eps bits, sample bits} each — a single predicated st.shared.v4 in the
   // streaming loop, and the patch pass touches no global memory for its reads
-  uint4* cand = reinterpret_cast<uint4*>(misc + MISC_WORDS);
+  // rowctr[w]: the next row trip of warp w's block of rows nobody has claimed yet (work stealing, see the streaming loop)
+  uint32_t* rowctr = misc + MISC_WORDS;
+  uint4* cand = reinterpret_cast<uint4*>(rowctr + ROWCTR_WORDS);
   const uint32_t cand_addr = (uint32_t)__cvta_generic_to_shared(cand);
   const uint32_t cand_cnt_addr = (uint32_t)__cvta_generic_to_shared(&misc[44]);
+  const uint32_t hb_addr = (uint32_t)__cvta_generic_to_shared(hb);
 
-  for (int j = tid; j < H0_WORDS + PRED_WORK_WORDS; j += THREADS) h0[j] = 0;
+  for (int j = tid; j < H0_WORDS + PRED_WORK_WORDS; j += THREADS) hp[j] = 0;
   if (tid < MISC_WORDS) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
+  if (tid < ROWCTR_WORDS) rowctr[tid] = 1u;      // trip 0 of every block is the pilot row
   __syncthreads();
   stamp(kp, 0);
 
@@ -109,25 +209,27 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
   const float post_M = p.post_M, inv_ah = p.inv_alpha_hat, inv_sa = kp.inv_sqrt_alpha_t;
   const int mode = p.moments_mode;
   const int centre_mode = SPEC ? 2 : ((mode == DU_MOM_CENTERED) ? 1 : ((mode == DU_MOM_VAR_WITH_CENTER) ? 2 : 0));
-  const int64_t srow = b * p.score_stride + base, erow = b * p.eps_stride + base, xrow = b * p.sample_stride + base;
+  // all row pointers address the IMAGE (not this CTA's slice): a warp may process rows of any CTA of its cluster (work stealing)
+  const int64_t srow = b * p.score_stride, erow = b * p.eps_stride, xrow = b * p.sample_stride;
   const T* eps_row = reinterpret_cast<const T*>(p.eps) + erow;
   const float* xs = reinterpret_cast<const float*>(p.sample) + xrow;
-  float* urow = p.unc_out + b * p.unc_stride + base;
-  float* prow = reinterpret_cast<float*>(p.prev_out) + b * p.prev_stride + base;
-  const float* Srow = (SPEC || p.S) ? (p.S + (p.S_broadcast ? 0 : b * p.S_stride) + base) : nullptr;
+  float* uimg = p.unc_out + b * p.unc_stride;
+  float* urow = uimg + base;                      // this CTA's slice of the map (the rare paths work per slice)
+  float* prow = reinterpret_cast<float*>(p.prev_out) + b * p.prev_stride;
+  const float* Srow = (SPEC || p.S) ? (p.S + (p.S_broadcast ? 0 : b * p.S_stride)) : nullptr;
   const bool has_S = SPEC ? true : (Srow != nullptr);
-  // mask by band as ONE unsigned compare: `higher`: key >= UB  <=>  key - UB < 2^32 - UB;  `lower`: key < LB  <=>  key - 0 < LB
-  uint32_t one_lo = 0, one_w = 0;
   const int ngroups = (int)(L / VEC);
   const int trips = (int)pk.trips;
   uint32_t nan_seen = 0;
-  uint32_t LB = 0, UB = 0;   // band in key space, known after the pilot
+  uint32_t below = 0;        // keys under the band seen by this thread
+  uint32_t LB = 0, W = 0, sh = 0;   // band [LB, LB + W) in key space and the shift of the fine bins, known after the pilot
+  // mask by band as ONE unsigned compare: `higher`: key >= UB  <=>  key - UB < 2^32 - UB;  `lower`: key < LB  <=>  key - 0 < LB
+  uint32_t one_lo = 0, one_w = 0;
   const uint64_t pol = pk.pol_stream;
 
-  // one group of VEC elements: map value (from the scores, or replayed from the slot), histogram, mask by band, update
-  auto do_group = [&](int g, bool valid, bool from_scores, bool pilot_only) {
+  // one group of VEC elements: map value (from the scores, or replayed from the slot), band bookkeeping, mask by band, update
+  auto do_group = [&](uint32_t g_elems /* first element of the group, in the image */, bool valid, bool from_scores, bool pilot_only) {
     float u[VEC], e0[VEC], s[VEC], Sv[VEC];
-    const uint32_t g_elems = (uint32_t)g * VEC;
     if (valid) {
       const uint32_t byte_off = g_elems * (uint32_t)sizeof(T);
       // eps was just read by du_batch_sum (evict-last): it comes from L2.  The pilot reads its rows once more later (normal
@@ -151,20 +253,21 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
 #pragma unroll
         for (int e = 0; e < VEC; ++e) u[e] = map_value(centre_mode, s1[e], s2[e], kp.inv_cnt, kp.inv_cm1);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-          nan_seen |= (u[e] != u[e]);
-          const uint32_t bin = __float_as_uint(u[e]) >> LOW;
-          const uint32_t inc = (bin & 1u) ? 0x10000u : 1u;
-          atomicAdd(&h0[bin >> 1], inc);
-          if (pilot_only) atomicAdd(&hp[bin >> 1], inc);
+        for (int e = 0; e < VEC; ++e) nan_seen |= (u[e] != u[e]);
+        if (pilot_only) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) {
+            const uint32_t bin = __float_as_uint(u[e]) >> LOW;
+            atomicAdd(&hp[bin >> 1], (bin & 1u) ? 0x10000u : 1u);
+          }
         }
 #pragma unroll
         for (int h = 0; h < VEC / 4; ++h)
-          *reinterpret_cast<float4*>(urow + g_elems + 4 * h) = make_float4(u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]);
+          *reinterpret_cast<float4*>(uimg + g_elems + 4 * h) = make_float4(u[4 * h], u[4 * h + 1], u[4 * h + 2], u[4 * h + 3]);
       } else {
 #pragma unroll
         for (int h = 0; h < VEC / 4; ++h) {   // replay: this thread wrote these values itself
-          const float4 u4 = *reinterpret_cast<const float4*>(urow + g_elems + 4 * h);
+          const float4 u4 = *reinterpret_cast<const float4*>(uimg + g_elems + 4 * h);
           u[4 * h] = u4.x; u[4 * h + 1] = u4.y; u[4 * h + 2] = u4.z; u[4 * h + 3] = u4.w;
         }
       }
@@ -180,16 +283,38 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       }
     }
     if (pilot_only) return;
-    // ---- band test and candidate entries first (while eps / sample are freshly unpacked: the streaming loop lives at the
-    // register limit, and every value kept alive across the update costs loads in flight), then mask, update, stores
+    // ---- band bookkeeping, all predicated (the loop has no data-dependent branch): keys under the band are counted, keys inside
+    // it go to the fine histogram and to the candidate list.  Keys are < 2^31 and so is LB: key - LB has its top bit set exactly
+    // when key < LB.
     uint32_t inband = 0;
     if (valid) {
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) inband |= (((__float_as_uint(u[e]) - LB) < (UB - LB)) ? 1u : 0u) << e;
+      for (int e = 0; e < VEC; ++e) {
+        const uint32_t d = __float_as_uint(u[e]) - LB;
+        below += d >> 31;
+        const uint32_t in = (d < W) ? 1u : 0u;
+        inband |= in << e;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.add.u32 [%0], %1;\n\t}"
+                     ::"r"(hb_addr + ((d >> sh) << 2)), "r"(1u), "r"(in) : "memory");
+      }
+    }
+    // Every in-band element is written provisionally with mask 0 (it lies below UB for `higher`, at or above LB for `lower`); the
+    // patch pass only has to overwrite those whose exact compare says 1.  Without the optional outputs the record therefore carries
+    // x_(t-1) FOR MASK 1, computed here where all operands are in registers (6 more instructions per element; the streaming loop
+    // is memory-bound), and the patch is a compare and a store.  With optional outputs it carries eps and the sample instead.
+    float pv1[VEC];
+    if constexpr (!OUTS) {
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float eg1, x01;
+          guided_elem(dc, post_M, inv_ah, inv_sa, u[e], e0[e], s[e], Sv[e], 1.0f, eg1, x01, pv1[e]);
+        }
+      }
     }
     {
-      // The streaming loop is issue-bound, so the append has no branches: one predicated shared-memory atomic per lane that has
-      // candidates (about a quarter of the lanes), then one predicated 16-byte store per candidate.  Order does not matter.
+      // one predicated shared-memory atomic per lane that has candidates (about a quarter of the lanes), then one predicated 16-byte
+      // store per candidate.  The order of the list does not matter.
       const uint32_t cnt = __popc(inband);
       uint32_t slot = 0;
       asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p atom.shared.add.u32 %0, [%1], %3;\n\t}"
@@ -200,8 +325,8 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
       for (int e = 0; e < VEC; ++e) {
         const uint32_t take = (room && (inband & (1u << e))) ? 1u : 0u;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
-                     ::"r"(cand_addr + slot * 16u), "r"(__float_as_uint(u[e])), "r"(g_elems + e), "r"(__float_as_uint(e0[e])),
-                       "r"(__float_as_uint(s[e])), "r"(take) : "memory");
+                     ::"r"(cand_addr + slot * 16u), "r"(__float_as_uint(u[e])), "r"(g_elems + e),
+                       "r"(__float_as_uint(OUTS ? e0[e] : pv1[e])), "r"(__float_as_uint(s[e])), "r"(take) : "memory");
         slot += take;
       }
     }
@@ -217,119 +342,138 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
         const int64_t o = g_elems + 4 * h;
         *reinterpret_cast<float4*>(prow + o) = make_float4(pv[4 * h], pv[4 * h + 1], pv[4 * h + 2], pv[4 * h + 3]);
         if constexpr (OUTS) {
-          if (p.x0_out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.x0_out) + b * p.x0_stride + base + o) =
+          if (p.x0_out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.x0_out) + b * p.x0_stride + o) =
               make_float4(x0v[4 * h], x0v[4 * h + 1], x0v[4 * h + 2], x0v[4 * h + 3]);
-          if (p.eps_out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.eps_out) + b * p.eps_out_stride + base + o) =
+          if (p.eps_out) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.eps_out) + b * p.eps_out_stride + o) =
               make_float4(eg[4 * h], eg[4 * h + 1], eg[4 * h + 2], eg[4 * h + 3]);
-          if (p.mask_out) *reinterpret_cast<float4*>(p.mask_out + b * p.mask_out_stride + base + o) =
+          if (p.mask_out) *reinterpret_cast<float4*>(p.mask_out + b * p.mask_out_stride + o) =
               make_float4(mk[4 * h], mk[4 * h + 1], mk[4 * h + 2], mk[4 * h + 3]);
         }
       }
     }
   };
-  auto group_of = [&](int j) { return ((warp * trips + j) << 5) | lane; };   // a warp owns `trips` consecutive rows of 32 groups
+  // A warp owns a BLOCK of `trips` consecutive rows of 32 groups in its CTA's slice; block (r, w) = warp w of CTA r.
+  constexpr int NWARPS = THREADS / 32;
+  auto row_group = [&](unsigned r, int w, int j, bool& valid) -> uint32_t {
+    const int g = ((w * trips + j) << 5) | lane;              // group index within the slice of CTA r
+    valid = g < ngroups;
+    return (uint32_t)r * (uint32_t)L + (uint32_t)g * VEC;     // first element, in the image
+  };
 
   // ---------------------------------------------------------------- pilot: trip 0, map values only
-  // The pilot (first loads of a cold launch, one cluster barrier, two rank searches) leaves HBM idle for a few microseconds:
-  // one lane per warp pulls the warp's next rows of every input into L2 meanwhile (a warp's rows are contiguous).
-  if (lane == 0 && pk.prefetch_rows > 0) {
-    const int row1 = warp * trips + 1;
-    const int rows = min((int)pk.prefetch_rows, min(trips - 1, ngroups / 32 - row1));
-    if (rows > 0) {
-      const size_t off = (size_t)row1 * 32 * VEC;   // elements
-      const uint32_t bytes_t = (uint32_t)rows * 32u * VEC * (uint32_t)sizeof(T), bytes_x = (uint32_t)rows * 32u * VEC * 4u;
-      for (int m = 0; m < p.M; ++m) prefetch_l2_bulk(reinterpret_cast<const T*>(p.scores[m]) + srow + off, bytes_t);
-      prefetch_l2_bulk(eps_row + off, bytes_t);
-      prefetch_l2_bulk(xs + off, bytes_x);
-    }
-  }
   {
-    const int g = group_of(0);
-    do_group(g, g < ngroups, true, true);
+    bool v;
+    const uint32_t ge = row_group(crank, warp, 0, v);
+    do_group(ge, v, true, true);
   }
   sync_all();   // pilot histograms of every CTA are complete
   locate_rank<H0_BINS, THREADS, false, true, true>(cluster, csize, hp, pk.r_lo, misc, pk.r_hi);
   const uint32_t lb_bin = pk.open_low ? 0u : misc[0];
   const uint32_t ub_bin = pk.open_high ? (uint32_t)H0_BINS : misc[1] + 1u;
-  if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // done with the peers' pilot histograms
   __syncthreads();
   LB = lb_bin << LOW;
-  UB = ub_bin << LOW;   // 4096 << 19 = 2^31: above every finite key and every NaN pattern with sign 0
-  one_lo = higher ? UB : 0u;
-  one_w = higher ? (0u - UB) : LB;   // (UB = 0 cannot occur: ub_bin >= 1)
+  W = (ub_bin << LOW) - LB;   // UB = 4096 << 19 = 2^31 when open at the top: above every finite key and every NaN pattern
+  sh = ((W - 1u) >> 10) ? (32u - (uint32_t)__clz((int)((W - 1u) >> 10))) : 0u;   // smallest shift with (W - 1) >> sh < 1024
+  one_lo = higher ? (LB + W) : 0u;
+  one_w = higher ? (0u - (LB + W)) : LB;   // (LB + W = 0 cannot occur: ub_bin >= 1)
   stamp(kp, 1);
 
   // ---------------------------------------------------------------- stream: every other trip, then the pilot replayed
   // Launched as the programmatic dependent of the du_batch_sum that produces S (S_overlap): everything above ran while that
   // kernel was still summing; its result is complete and visible from here on.  A no-op for an ordinary launch.
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int j = 1; j < trips; ++j) {
-    const int g = group_of(j);
-    do_group(g, g < ngroups, true, false);
+  if (kp.late_ns != 0) {
+    // test knob (DU_FUSED_JITTER_NS / DU_FUSED_JITTER_SEED): every CTA starts its streaming pass after a pseudo-random delay, so
+    // that rows get stolen in ever different patterns; the outputs must not depend on it (tests/test_fused_gpu.py stress test)
+    uint32_t h = (uint32_t)(blockIdx.y * gridDim.x + blockIdx.x) * 2654435761u ^ kp.late_from;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const unsigned long long wait_ns = h % kp.late_ns;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    do {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    } while (t - t0 < wait_ns);
+  }
+  // Row trips are CLAIMED, one at a time, from the block's counter (a shared-memory atomic by lane 0): first the warp's own block,
+  // then — HBM arbitration is not fair across SMs, the two CTAs of a cluster finish their own rows microseconds apart, and the
+  // finish needs both — the unclaimed rows of the other blocks of the cluster, the other CTAs' first (DSMEM atomics).  Every
+  // per-element structure (fine histogram, candidate records, counts) is addressed by image element, so a row may be processed
+  // by any CTA of the cluster; histograms and counts are summed over the cluster anyway.
+  auto claim = [&](uint32_t* ctr) -> int {
+    uint32_t j = 0;
+    if (lane == 0) j = atomicAdd(ctr, 1u);
+    return (int)__shfl_sync(0xffffffffu, j, 0);
+  };
+  for (int j = claim(&rowctr[warp]); j < trips;) {
+    const int j_next = claim(&rowctr[warp]);    // (claimed one trip ahead: the atomic's latency hides behind this trip's loads)
+    bool v;
+    const uint32_t ge = row_group(crank, warp, j, v);
+    do_group(ge, v, true, false);
+    j = j_next;
   }
   {
-    const int g = group_of(0);
-    do_group(g, g < ngroups, false, false);
+    bool v;
+    const uint32_t ge = row_group(crank, warp, 0, v);
+    do_group(ge, v, false, false);
+  }
+  if (pk.steal) {
+    for (unsigned i = 1; i <= csize; ++i) {            // the other CTAs first, this CTA's other warps last
+      const unsigned r = (crank + i) % csize;
+      uint32_t* vc = peer(rowctr, r);
+      for (;;) {
+        // one pass over the victim CTA's counters: lane l looks at block (warp + l) % NWARPS
+        const int vw = (warp + lane) % NWARPS;
+        const uint32_t seen = (lane < NWARPS) ? vc[vw] : 0xffffffffu;
+        const uint32_t open = __ballot_sync(0xffffffffu, seen < (uint32_t)trips);
+        if (open == 0u) break;
+        const int pick = (warp + (__ffs((int)open) - 1)) % NWARPS;
+        const int j = claim(vc + pick);
+        if (j >= trips) continue;                      // somebody else took the block's last row meanwhile: look again
+        bool v;
+        const uint32_t ge = row_group(r, pick, j, v);
+        do_group(ge, v, true, false);
+      }
+    }
   }
   if (__any_sync(0xffffffffu, nan_seen) && lane == 0) misc[3] = 1u;
+  below = __reduce_add_sync(0xffffffffu, below);
+  if (lane == 0) atomicAdd(&misc[46], below);
   stamp(kp, 2);
-  if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // nobody reads this CTA's pilot histogram any more
-  for (int j = tid; j < PRED_WORK_WORDS; j += THREADS) work[j] = 0;
 
   // ---------------------------------------------------------------- finish: verify the band, exact select, patch
-  sync_all();   // full histograms, candidate lists and flags of every CTA are complete
+  sync_all();   // fine histograms, counts, candidate lists and flags of every CTA are complete; nobody reads a pilot histogram any more
   bool bad = false;
+  uint32_t below_tot = 0, in_tot = 0;
   for (unsigned r = 0; r < csize; ++r) {
     const uint32_t* pm = peer(misc, r);
     bad |= (pm[3] != 0u) | (pm[45] != 0u);
+    below_tot += pm[46];
+    in_tot += pm[44];
   }
-  uint32_t d0 = 0, below0 = 0;
-  if (!bad) {
-    locate_rank<H0_BINS, THREADS, false, true>(cluster, csize, h0, kp.lo, misc);
-    d0 = misc[0]; below0 = misc[1];
-    const uint32_t cnt0 = misc[2];
-    __syncthreads();
-    bad = !(d0 >= lb_bin && d0 < ub_bin) || cnt0 > (uint32_t)PRED_LIST_CAP;
-  }
+  // rank lo must fall inside the band (this is the verification of the prediction)
+  bad |= !(kp.lo >= below_tot && kp.lo - below_tot < in_tot);
   stamp(kp, 3);
-  float thr;
+  float thr = 0.0f;
   bool redo = false;
-  if (bad) {
-    // exact select over the map in its slot (L2) and a full update pass (`bad` is identical in every CTA of the cluster)
-    thr = select_threshold<THREADS>(cluster, csize, crank, kp, urow, h0, work, misc);
-    redo = true;
-  } else {
-    uint32_t* list = work;
-    uint32_t* h1 = work + PRED_LIST_CAP;
-    const uint32_t want = d0 << LOW;
-    const uint32_t ncand = misc[44];
-    for (uint32_t i = tid; i < ncand; i += THREADS) {
-      const uint32_t key = cand[i].x;
-      if ((key >> LOW) == d0) {
-        list[atomicAdd(&misc[6], 1u)] = key;
-        atomicAdd(&h1[(key >> H2_BITS) & (H1_BINS - 1)], 1u);
-      }
-    }
-    sync_all();   // key lists and level-1 histograms complete
-    stamp(kp, 4);
-    bool has_nan = false;
+  uint32_t ncand = 0;
+  if (!bad) {
+    ncand = misc[44];
     const bool need_next = kp.hi > kp.lo;
-    list_select<THREADS>(cluster, csize, crank, kp, h0, list, h1, misc, want, below0, has_nan);
-    const uint32_t key_lo = misc[41];
-    uint32_t key_hi = misc[43];
-    if (need_next && key_hi == 0xffffffffu) {
-      // the successor lives in a higher level-0 bin: smallest candidate key above key_lo, cluster-wide ...
-      if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
-      uint32_t best = 0xffffffffu;
-      for (uint32_t i = tid; i < ncand; i += THREADS) { const uint32_t key = cand[i].x; if (key > key_lo) best = min(best, key); }
-      best = __reduce_min_sync(0xffffffffu, best);
-      if (lane == 0 && best != 0xffffffffu) atomicMin(&misc[4], best);
-      sync_all();
-      for (unsigned r = 0; r < csize; ++r) key_hi = min(key_hi, peer(misc, r)[4]);
-      if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
-      if (key_hi == 0xffffffffu) {
-        // ... or above the band: one pass over the map in its slot
+    bad = !band_select<THREADS>(cluster, csize, crank, kp, hp, cand, hb, misc, LB, sh, kp.lo - below_tot);
+    if (bad) {
+      if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");   // (band_select left an arrival pending)
+    } else {
+      const uint32_t key_lo = misc[41];
+      uint32_t key_hi = misc[43];
+      if (need_next && key_hi == 0xffffffffu) {
+        // the successor lies above the band: smallest key above key_lo, one pass over the map in its slot, cluster-wide.  Rows of
+        // this slice may have been written by another CTA of the cluster (work stealing): fence - barrier - fence orders them.
         if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+        __threadfence();
+        sync_all();
+        __threadfence();
+        uint32_t best = 0xffffffffu;
         const int ng4 = (int)(L / 4);
         for (int g = tid; g < ng4; g += THREADS) {
           const uint4 v = *reinterpret_cast<const uint4*>(urow + 4 * g);
@@ -344,37 +488,77 @@ __global__ void __launch_bounds__(THREADS, MINB) fused_pred_kernel(const __grid_
         if (csize > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
         redo = true;   // elements at key_hi were decided without the exact compare
       }
+      thr = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, p.lerp_fma);
     }
-    thr = lerp_torch(__uint_as_float(key_lo), __uint_as_float(key_hi), kp.w, p.lerp_fma);
-    stamp(kp, 5);
-    if (!redo) {
-      // ---- patch the candidates with the exact compare (all inputs come from the shared-memory stash)
+  }
+  stamp(kp, 5);
+  if (bad) {
+    // exact select over the map in its slot (L2) and a full update pass (`bad` is identical in every CTA of the cluster).  The
+    // level-0 histogram the select starts from is rebuilt here; peers are past their DSMEM reads of this CTA's areas (barrier),
+    // and the map / provisional x_(t-1) values another CTA wrote into this slice (work stealing) are ordered by fence - barrier - fence.
+    __threadfence();
+    sync_all();
+    __threadfence();
+    for (int j = tid; j < H0_WORDS + PRED_WORK_WORDS; j += THREADS) hp[j] = 0;
+    if (tid == 0) { misc[4] = 0xffffffffu; misc[5] = 0u; misc[6] = 0u; misc[40] = 0u; }
+    __syncthreads();
+    const int ng4 = (int)(L / 4);
+    for (int g = tid; g < ng4; g += THREADS) {
+      const uint4 v = *reinterpret_cast<const uint4*>(urow + 4 * g);
+      const uint32_t kk[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t bin = kk[e] >> LOW;
+        atomicAdd(&hp[bin >> 1], (bin & 1u) ? 0x10000u : 1u);
+      }
+    }
+    thr = select_threshold<THREADS>(cluster, csize, crank, kp, urow, hp, work, misc);
+    redo = true;
+  }
+  if (!redo) {
+    // ---- patch the candidates with the exact compare (all inputs come from the shared-memory records)
+    if constexpr (!OUTS) {
       for (uint32_t i = tid; i < ncand; i += THREADS) {
         const uint4 rec = cand[i];
         const float u = __uint_as_float(rec.x);
-        const int64_t o = rec.y;
-        const float mk = (higher ? (u > thr) : (u < thr)) ? 1.0f : 0.0f;
-        float eg, x0, pv;
-        const float e0 = __uint_as_float(rec.z);
-        const float Sv = has_S ? ld_coherent_f1(Srow + o) : e0;   // the S row is shared by every image of the batch: L2 / L1 resident
-        guided_elem(dc, post_M, inv_ah, inv_sa, u, e0, __uint_as_float(rec.w), Sv, mk, eg, x0, pv);
-        prow[o] = pv;
-        if constexpr (OUTS) {
-          if (p.x0_out) reinterpret_cast<float*>(p.x0_out)[b * p.x0_stride + base + o] = x0;
-          if (p.eps_out) reinterpret_cast<float*>(p.eps_out)[b * p.eps_out_stride + base + o] = eg;
-          if (p.mask_out) p.mask_out[b * p.mask_out_stride + base + o] = mk;
+        if (higher ? (u > thr) : (u < thr)) prow[rec.y] = __uint_as_float(rec.z);
+      }
+    } else {
+      for (uint32_t i0 = tid; i0 < ncand; i0 += 4 * THREADS) {
+        uint4 rec[4];
+        float Sv[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {   // records and S values first: four independent L2 / shared-memory reads in flight per thread
+          const uint32_t i = i0 + q4 * THREADS;
+          rec[q4] = (i < ncand) ? cand[i] : make_uint4(0u, 0u, 0u, 0u);
+          Sv[q4] = (has_S && i < ncand) ? ld_coherent_f1(Srow + rec[q4].y) : __uint_as_float(rec[q4].z);   // (the S row is shared by the batch: L2 / L1 resident)
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (i0 + q4 * THREADS < ncand) {
+            const float u = __uint_as_float(rec[q4].x);
+            const int64_t o = rec[q4].y;
+            const float mk = (higher ? (u > thr) : (u < thr)) ? 1.0f : 0.0f;
+            float eg, x0, pv;
+            guided_elem(dc, post_M, inv_ah, inv_sa, u, __uint_as_float(rec[q4].z), __uint_as_float(rec[q4].w), Sv[q4], mk, eg, x0, pv);
+            prow[o] = pv;
+            if (p.x0_out) reinterpret_cast<float*>(p.x0_out)[b * p.x0_stride + o] = x0;
+            if (p.eps_out) reinterpret_cast<float*>(p.eps_out)[b * p.eps_out_stride + o] = eg;
+            if (p.mask_out) p.mask_out[b * p.mask_out_stride + o] = mk;
+          }
         }
       }
     }
+  } else {
+    guided_update_slice<T, THREADS, true, false>(kp, urow, thr, b, base, 0u);
   }
-  if (redo) guided_update_slice<T, THREADS, true, false>(kp, urow, thr, b, base, 0u);
   if (crank == 0 && tid == 0 && p.thr_out) p.thr_out[b] = thr;
   stamp(kp, 6);
   if (csize > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
 }
 
 
-static constexpr size_t kPredFixedBytes = (size_t)(H0_WORDS + PRED_WORK_WORDS + MISC_WORDS) * 4;
+static constexpr size_t kPredFixedBytes = (size_t)(H0_WORDS + PRED_WORK_WORDS + MISC_WORDS + ROWCTR_WORDS) * 4;
 
 template <typename T, int MT>
 constexpr bool pred_narrow() { return sizeof(T) == 2 && MT > 0; }
@@ -431,8 +615,8 @@ static int launch_pred_m(const PredKParams& pk, const FusedPlan& plan, int threa
   return launch_pred_t<T, MT, 512, 2, OUTS>(pk, plan, smem, st);
 #else
   switch (threads) {
-#ifdef DU_PRED_TUNING   // 1024-thread and 384 / 768-thread CTAs (80 registers): measured slower, kept for sweeps only (csrc/build.sh -DDU_PRED_TUNING)
     case 1024: return launch_pred_t<T, MT, 1024, 1, OUTS>(pk, plan, smem, st);
+#ifdef DU_PRED_TUNING   // 384 / 768-thread CTAs (80 registers): measured slower, kept for sweeps only (csrc/build.sh -DDU_PRED_TUNING)
     case 768: return launch_pred_t<T, MT, 768, 1, OUTS>(pk, plan, smem, st);
     case 384: return launch_pred_t<T, MT, 384, 2, OUTS>(pk, plan, smem, st);
 #endif
@@ -457,34 +641,17 @@ static int launch_pred(const PredKParams& pk, const FusedPlan& plan, int threads
   }
 }
 
-int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
-  const du_fused_params& p = kp.p;
-  // DU_FUSED_PRED=0 forces the three-phase kernel; DU_FUSED_BAND_SIGMA=<x> sets the half-width of the rank window in
-  // standard deviations of the pilot quantile (default 6)
-  const char* e_p = getenv("DU_FUSED_PRED");
-  if (e_p && atoi(e_p) == 0) return 0;
-  const bool fast_c = p.ddim.prediction_type == DU_PRED_EPSILON && !p.ddim.use_clipped_model_output &&
-                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32 && !p.skip_ddim;
-  if (!fast_c || (plan.threads != 512 && plan.threads != 1024)) return 0;
-  // elements per thread and trip: 4, except 16-bit scores with a runtime-M instance (16-byte vectors of 8)
+// One attempt with a given launch shape: returns 1 if launched, 0 if the shape is not eligible, < 0 on error.
+static int try_pred(const FusedKParams& kp_in, int cluster, int threads, int64_t min_trips, cudaStream_t st) {
+  const du_fused_params& p = kp_in.p;
   const bool outs_req = p.x0_out || p.eps_out || p.mask_out;
   const bool mt_known = outs_req ? (p.M == 5) : (p.M == 4 || p.M == 5 || p.M == 8 || p.M == 16);   // mirrors launch_pred
+  // elements per thread and trip: 4, except 16-bit scores with a runtime-M instance (16-byte vectors of 8)
   const int vec = (p.score_dtype == DU_F32 || mt_known) ? 4 : 8;
-  const int64_t L = kp.L, ngroups = L / vec;
-  if (L >= 65536) return 0;   // packed 16-bit level-0 counters
-  // Threads per CTA: the plan's (512 x 2 CTAs or 1024 x 1 per SM, 64 registers).  384 / 768 threads with 80 registers keep
-  // all M + 3 loads of a trip in one batch but measured slower (54.1 vs 49.3 us on the ImageNet-128 step): the loop is
-  // closer to issue-bound than to latency-bound.  DU_FUSED_PRED_THREADS=<384|512|768|1024> overrides.
-  int threads = plan.threads;
-  if (const char* e_t = getenv("DU_FUSED_PRED_THREADS")) {
-    const int t = atoi(e_t);
-    if (t == 384 || t == 512 || t == 768 || t == 1024) threads = t;
-  }
+  if (p.n % ((int64_t)cluster * vec) != 0) return 0;
+  const int64_t L = p.n / cluster, ngroups = L / vec;
+  if (L >= 65536) return 0;   // packed 16-bit level-0 counters (pilot histogram, fallback)
   const int64_t trips = (ngroups + threads - 1) / threads;
-  // The pilot (~4 us) and the latency-bound finish (~8 us) are fixed costs: below ~8 trips per thread the three-phase kernel
-  // is faster (ImageNet-64, b128: 17.4 us against 18.8 us), above it the single pass wins (ImageNet-128: 49.2 against 54.3).
-  const char* e_m = getenv("DU_FUSED_PRED_MIN_TRIPS");
-  const int64_t min_trips = (e_m && atoi(e_m) >= 4) ? atoi(e_m) : 8;
   if (trips < min_trips) return 0;
   // pilot sample: trip 0 of every warp = row (warp * trips) of 32 groups
   int64_t pilot_groups = 0;
@@ -492,16 +659,25 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
     const int64_t left = ngroups - (int64_t)w * trips * 32;
     pilot_groups += left <= 0 ? 0 : (left < 32 ? left : 32);
   }
-  const double n_p = (double)pilot_groups * vec * plan.cluster;
+  const double n_p = (double)pilot_groups * vec * cluster;
   if (n_p < 256) return 0;
+  // DU_FUSED_BAND_SIGMA=<x>: half-width of the rank window in standard deviations of the pilot quantile.  Default 5: the band is
+  // missed by one image in ~2 million (it then takes the exact fallback, +20 us for that launch); 6 costs 0.4 us per launch, 4 gains 0.4.
   const char* e_s = getenv("DU_FUSED_BAND_SIGMA");
-  const double nsig = (e_s && atof(e_s) > 0.0) ? atof(e_s) : 6.0;
+  const double nsig = (e_s && atof(e_s) > 0.0) ? atof(e_s) : 5.0;
   const double q = (double)p.q;
   const double rank_p = q * (n_p - 1.0);
   const double delta = nsig * std::sqrt(n_p * q * (1.0 - q)) + 4.0;
   PredKParams pk;
-  pk.k = kp;
+  pk.k = kp_in;
+  pk.k.L = L;
   pk.k.tmem_cols = 0; pk.k.tmem_cpg = 0;
+  pk.k.late_ns = 0; pk.k.late_from = 0;
+  if (const char* e_j = getenv("DU_FUSED_JITTER_NS")) {
+    pk.k.late_ns = (uint32_t)atoi(e_j);
+    const char* e_js = getenv("DU_FUSED_JITTER_SEED");
+    pk.k.late_from = e_js ? (uint32_t)atoi(e_js) * 747796405u + 1u : 1u;
+  }
   pk.trips = (uint32_t)trips;
   pk.open_low = (rank_p - delta <= 0.0) ? 1u : 0u;
   pk.open_high = (rank_p + delta >= n_p - 1.0) ? 1u : 0u;
@@ -509,8 +685,8 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
   pk.r_hi = pk.open_high ? (uint32_t)(n_p - 1.0) : (uint32_t)std::ceil(rank_p + delta);
   // candidate list: the band holds about 2 * delta / n_p of the elements plus two level-0 bins; room for 1.6x that, and
   // no more: global loads in flight are buffered in L1, which shares the SM's 256 KB with shared memory, so a large
-  // shared-memory footprint throttles the streaming pass (measured: 2 x 116 KB per SM cost 10 us against 2 x 78 KB).
-  // DU_FUSED_SMEM_KB caps the per-CTA footprint (default 64).
+  // shared-memory footprint throttles the streaming pass (measured: 2 x 116 KB per SM cost 10 us against 2 x 78 KB, and 2 x 48 KB
+  // — a list that overflows — 15 us).  DU_FUSED_SMEM_KB caps the per-CTA footprint (default 64, twice that for one CTA per SM).
   const char* e_k = getenv("DU_FUSED_SMEM_KB");
   const size_t cap_bytes = (size_t)((e_k && atoi(e_k) > 0) ? atoi(e_k) : 64) * 1024;
   const size_t kMax = 227 * 1024, kHalf = 113 * 1024;
@@ -526,20 +702,60 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
   if (cap < 256) return 0;
   pk.cand_max = (uint32_t)cap;
   {
-    const char* e_r = getenv("DU_FUSED_PREFETCH_ROWS");
-    pk.prefetch_rows = e_r ? (uint32_t)atoi(e_r) : 0u;   // measured: the extra traffic delays the pilot more than it saves
+    const char* e_r = getenv("DU_FUSED_STEAL");
+    pk.steal = (e_r && atoi(e_r) == 0) ? 0u : 1u;
   }
   {
     // DU_L2_HINTS=0: every load at normal priority (A/B of the eviction hints)
     const char* e_h = getenv("DU_L2_HINTS");
     pk.pol_stream = (e_h && atoi(e_h) == 0) ? kL2EvictNormal : kL2EvictFirst;
   }
+  FusedPlan plan{};
+  plan.cluster = cluster; plan.threads = threads; plan.minb = one_cta ? 1 : 2;
   const size_t smem = kPredFixedBytes + (size_t)cap * 16;
   switch (p.score_dtype) {
     case DU_F32: return launch_pred<float>(pk, plan, threads, smem, st);
     case DU_F16: return launch_pred<__half>(pk, plan, threads, smem, st);
     default: return launch_pred<__nv_bfloat16>(pk, plan, threads, smem, st);
   }
+}
+
+int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_t st) {
+  const du_fused_params& p = kp.p;
+  // DU_FUSED_PRED=0 forces the three-phase kernel
+  const char* e_p = getenv("DU_FUSED_PRED");
+  if (e_p && atoi(e_p) == 0) return 0;
+  const bool fast_c = p.ddim.prediction_type == DU_PRED_EPSILON && !p.ddim.use_clipped_model_output &&
+                      p.sample_dtype == DU_F32 && p.prev_dtype == DU_F32 && !p.skip_ddim;
+  if (!fast_c) return 0;
+  // The pilot (~3.5 us) and the latency-bound finish (~6 us) are fixed costs: below ~6 trips per thread the three-phase kernel is
+  // faster (ImageNet-64 b128, 6 trips: 17.9 us against 18.7 us; U-ViT latents, 4 trips at most: the three-phase kernel)
+  const char* e_m = getenv("DU_FUSED_PRED_MIN_TRIPS");
+  const int64_t min_trips = (e_m && atoi(e_m) >= 4) ? atoi(e_m) : 6;
+  // Launch shape.  The kernel keeps no copy of the map in shared memory, so it does not need the three-phase kernel's cluster
+  // plan: ONE CTA of 1024 threads per image (no cluster barrier, no DSMEM, no wait for a peer CTA on a busier SM) is the
+  // fastest shape measured (ImageNet-128 step: 44.6 us against 47.4 us for clusters of two 512-thread CTAs), then 2 x 512, then
+  // the three-phase plan's shape.  DU_FUSED_CLUSTER / DU_FUSED_THREADS / DU_FUSED_PRED_THREADS pin it (tests, sweeps).
+  const char* e_c = getenv("DU_FUSED_CLUSTER");
+  const char* e_t = getenv("DU_FUSED_THREADS");
+  const char* e_pt = getenv("DU_FUSED_PRED_THREADS");
+  const bool pinned = (e_c && atoi(e_c) > 0) || (e_t && atoi(e_t) > 0) || (e_pt && atoi(e_pt) > 0);
+  if (pinned) {
+    int threads = plan.threads;
+    if (e_pt) {
+      const int t = atoi(e_pt);
+      if (t == 384 || t == 512 || t == 768 || t == 1024) threads = t;
+    }
+    if (threads != 384 && threads != 512 && threads != 768 && threads != 1024) return 0;
+    return try_pred(kp, plan.cluster, threads, min_trips, st);
+  }
+  const int shapes[3][2] = {{1, 1024}, {2, 512}, {plan.cluster, plan.threads}};
+  for (int i = 0; i < 3; ++i) {
+    if (shapes[i][1] != 512 && shapes[i][1] != 1024) continue;
+    const int rc = try_pred(kp, shapes[i][0], shapes[i][1], min_trips, st);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 }  // namespace du

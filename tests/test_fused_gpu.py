@@ -428,3 +428,45 @@ def test_host_streamed_steps_pipeline_across_calls(ops):
         hs.synchronize()
         for j in range(calls):
             assert bits_equal(outs[j][0], wants[j]["prev"]) and bits_equal(outs[j][1], wants[j]["u"]), (rep, j)
+
+
+def test_fused_predictive_kernel_work_stealing_stress(ops, monkeypatch):
+    """Race evidence for the cluster kernels: the CTAs of every cluster start their streaming pass after
+    pseudo-random delays (DU_FUSED_JITTER_NS), so the rows of an image are claimed — and stolen across the cluster through DSMEM
+    atomics — in a different pattern on every launch.  400 launches, all outputs must be bit-identical to the undisturbed launch,
+    to the launch without stealing and to the three-phase kernel."""
+    eps, scores, sample = synth(6, 3, 128, 5, seed=77)
+    d = dev()
+    _, k = coeffs_for(ops, 300, 280)
+    sg, eg, xg = [s.to(d) for s in scores], eps.to(d), sample.to(d)
+    S = ops.batch_sum(eg)
+
+    def run():
+        r = ops.fused_uncertainty_step(sg, eg, xg, 0.9, k, 0.5, S=S, S_broadcast=True, want_x0=False)
+        torch.cuda.synchronize()
+        return [r[n].clone().view(torch.int32) for n in ("prev", "u", "thr")]
+
+    base = run()
+    assert ops.fused_last_kernel() == "fused_pred_kernel"
+    monkeypatch.setenv("DU_FUSED_STEAL", "0")
+    for a, b in zip(base, run()):
+        assert torch.equal(a, b)
+    monkeypatch.delenv("DU_FUSED_STEAL")
+    monkeypatch.setenv("DU_FUSED_PRED", "0")
+    ref = run()
+    assert ops.fused_last_kernel() == "fused_step_kernel"
+    for a, b in zip(base, ref):
+        assert torch.equal(a, b)
+    monkeypatch.delenv("DU_FUSED_PRED")
+    monkeypatch.setenv("DU_FUSED_PRED_MIN_TRIPS", "4")     # (clusters of 4 leave 6 trips per thread)
+    for cluster in ("", "1", "2", "4"):                      # "" = the default shape: one CTA of 1024 threads per image
+        if cluster:
+            monkeypatch.setenv("DU_FUSED_CLUSTER", cluster)
+            monkeypatch.setenv("DU_FUSED_THREADS", "512")
+        for it in range(100):
+            monkeypatch.setenv("DU_FUSED_JITTER_NS", str(2000 + 400 * (it % 40)))
+            monkeypatch.setenv("DU_FUSED_JITTER_SEED", str(it))
+            got = run()
+            assert ops.fused_last_kernel() == "fused_pred_kernel"
+            for a, b in zip(base, got):
+                assert torch.equal(a, b), f"launch {it} (cluster {cluster or 'auto'}) differs"

@@ -126,8 +126,10 @@ def test_second_order_momentum_kernel():
     new, corrected, root = second_order_momentum_update(mom, u, i, beta)
     want = beta * mom + (1 - beta) * u
     assert torch.equal(new, want)
-    wc = (want.cpu() / (1 - beta ** i + 1e-5))        # CPU true division, one rounding
-    assert torch.equal(corrected.cpu(), wc) and torch.equal(root.cpu(), torch.sqrt(wc))
+    # (torch divides a tensor by a Python scalar as a multiplication by its reciprocal; the kernel divides: last-bit differences)
+    wc = want.double().cpu() / (1 - beta ** i + 1e-5)
+    assert float(((corrected.double().cpu() - wc).abs() / wc.abs().clamp_min(1e-30)).max()) < 2e-7
+    assert float(((root.double().cpu() - wc.sqrt()).abs() / wc.sqrt().clamp_min(1e-30)).max()) < 2e-7
     first, _, _ = second_order_momentum_update(None, u, 0, beta)
     assert torch.equal(first, u)
 
@@ -220,4 +222,4 @@ def test_guidance_function_posterior_is_one_fused_launch():
     assert np.array_equal(fus["thr"].cpu().numpy(), torch.quantile(fus["u"].cpu().flatten(1), 0.9, dim=1).numpy())
     assert torch.equal(fus["mask"], (fus["u"] > fus["thr"].view(-1, 1, 1, 1)).float())
     assert close_frac(fus["eps"], ref["eps"]) < 0.002          # (a pixel on the threshold may flip with the map's last bit)
-    assert torch.equal(out, fus["eps"])
+    assert torch.equal(out.view(torch.int32), fus["eps"].view(torch.int32))     # (bit patterns: u = 0 gives NaN, as in the reference)
