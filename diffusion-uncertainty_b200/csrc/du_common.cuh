@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #include "../../include/du_b200.h"
 
@@ -395,12 +396,29 @@ __device__ __forceinline__ DdimOut ddim_update(float mo, float x, float noise, c
 
 // ---- launch geometry --------------------------------------------------------------------------------
 struct RowGrid { dim3 grid; dim3 block; };
+// The elementwise kernels loop grid-stride in both dimensions, so the grid is capped at a few resident waves' worth of CTAs
+// (148 SMs x DU_ROWS_CTAS_PER_SM, default 16; 0 = one CTA per 256 groups as before): thousands of CTAs that each live for a
+// microsecond spend their time being launched.
+inline int rows_cta_cap() {
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("DU_ROWS_CTAS_PER_SM");
+    cap = 148 * ((e && atoi(e) >= 0) ? atoi(e) : 16);
+  }
+  return cap;
+}
 inline RowGrid row_grid(int64_t B, int64_t n_items_per_row, int threads) {
   RowGrid g;
   g.block = dim3(threads);
   int64_t gx = (n_items_per_row + threads - 1) / threads;
   if (gx < 1) gx = 1;
-  g.grid = dim3((unsigned)gx, (unsigned)(B < 65535 ? B : 65535));
+  int64_t gy = B < 65535 ? B : 65535;
+  const int64_t cap = rows_cta_cap();
+  if (cap > 0 && gx * gy > cap) {
+    if (gy >= cap) { gx = 1; gy = cap; }
+    else { gx = (cap + gy - 1) / gy; }
+  }
+  g.grid = dim3((unsigned)gx, (unsigned)gy);
   return g;
 }
 

@@ -49,32 +49,44 @@ __global__ void __launch_bounds__(kRngBlock, 4)
 perturb_randn_kernel(const void* __restrict__ x, int x_dtype, int64_t N, uint64_t seed, uint64_t offset,
                      const uint64_t* __restrict__ state, float a, float b, void* __restrict__ out, int out_dtype,
                      void* __restrict__ noise_out, int noise_dtype) {
-  if (state) { seed = state[0]; offset = state[1]; }
+  if (state) { seed = state[0]; offset += state[1]; }   // device-resident state: the host `offset` is an extra offset on top of it
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)blockDim.x * gridDim.x;
   curandStatePhilox4_32_10_t st;
   curand_init(seed, (unsigned long long)v, offset, &st);
-  for (int64_t base = v; base < N; base += stride * kRngUnroll) {
-    float xv[kRngUnroll];
+  // Two of torch's loop iterations per trip (KU = 2): the 8 loads of both are issued before the first Philox round, which doubles
+  // the bytes in flight per thread — the kernel is bound by memory-level parallelism at 4 CTAs per SM (59 registers), not by the
+  // Philox / Box-Muller arithmetic.  The element <-> variate mapping is untouched: iteration k of virtual thread v still gets
+  // the k-th curand_normal4 of subsequence v.
+  constexpr int KU = 2;
+  for (int64_t base = v; base < N; base += stride * kRngUnroll * KU) {
+    float xv[KU][kRngUnroll];
     if (HAS_X) {
 #pragma unroll
-      for (int ii = 0; ii < kRngUnroll; ++ii) {
-        const int64_t li = base + stride * ii;
-        xv[ii] = li < N ? load1(x, li, x_dtype) : 0.f;
+      for (int k = 0; k < KU; ++k) {
+#pragma unroll
+        for (int ii = 0; ii < kRngUnroll; ++ii) {
+          const int64_t li = base + stride * (kRngUnroll * k + ii);
+          xv[k][ii] = li < N ? load1(x, li, x_dtype) : 0.f;
+        }
       }
     }
-    const float4 r4 = curand_normal4(&st);
-    const float r[kRngUnroll] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-    for (int ii = 0; ii < kRngUnroll; ++ii) {
-      const int64_t li = base + stride * ii;
-      if (li >= N) continue;
-      // torch: static_cast<scalar_t>(rand * std + mean) with std = 1, mean = 0, then the tensor's dtype
-      float nz = __fmaf_rn(r[ii], 1.0f, 0.0f);
-      if (noise_dtype == DU_F16) nz = __half2float(__float2half_rn(nz));
-      else if (noise_dtype == DU_BF16) nz = __bfloat162float(__float2bfloat16_rn(nz));
-      if (noise_out) store1(noise_out, li, noise_dtype, nz);
-      if (HAS_X) store1(out, li, out_dtype, __fadd_rn(__fmul_rn(a, xv[ii]), __fmul_rn(b, nz)));   // as PerturbF (du_step.cu)
+    for (int k = 0; k < KU; ++k) {
+      if (base + stride * kRngUnroll * k >= N) break;
+      const float4 r4 = curand_normal4(&st);
+      const float r[kRngUnroll] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+      for (int ii = 0; ii < kRngUnroll; ++ii) {
+        const int64_t li = base + stride * (kRngUnroll * k + ii);
+        if (li >= N) continue;
+        // torch: static_cast<scalar_t>(rand * std + mean) with std = 1, mean = 0, then the tensor's dtype
+        float nz = __fmaf_rn(r[ii], 1.0f, 0.0f);
+        if (noise_dtype == DU_F16) nz = __half2float(__float2half_rn(nz));
+        else if (noise_dtype == DU_BF16) nz = __bfloat162float(__float2bfloat16_rn(nz));
+        if (noise_out) store1(noise_out, li, noise_dtype, nz);
+        if (HAS_X) store1(out, li, out_dtype, __fadd_rn(__fmul_rn(a, xv[k][ii]), __fmul_rn(b, nz)));   // as PerturbF (du_step.cu)
+      }
     }
   }
 }

@@ -1,8 +1,8 @@
 // du_select.cu — F2a: per-row linear-interpolated quantile, bit-identical to torch.quantile(..., dim=1).
 //
 // Exact order statistics by MSB-first radix select on order-preserving uint32 keys.  This file holds
-// the reference-grade exact path (one CTA per row, four 8-bit passes over the L2-resident row);
-// the fused step (du_fused.cu) selects inside distributed shared memory instead.
+// the unfused exact path, one CTA per row: a two-pass select with compaction (default) and the four-pass 8-bit select it falls
+// back to under heavy ties; the fused step (du_fused.cu) selects inside distributed shared memory instead.
 #include "du_common.cuh"
 
 namespace du {
@@ -97,21 +97,189 @@ __device__ void select_row_exact(const float* __restrict__ r, int64_t n, bool ve
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) quantile_rows_kernel(const float* __restrict__ u, int64_t B, int64_t n, int64_t stride,
-                                                             uint32_t lo, uint32_t hi, float w, int lerp_fma,
-                                                             float* __restrict__ thr_out, int32_t* __restrict__ rank_out,
-                                                             float* __restrict__ val_out) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t sh[8];
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-pass select (the default): pass 1 histograms the top 11 key bits of the row (2048 bins) and locates the bin of rank lo;
+// pass 2 compacts that bin's keys (typically 1-3 % of the row) into shared memory and remembers the smallest key above the bin;
+// two more histogram levels (11 + 10 bits) over the LIST finish the select, warp 0 ranks the handful of keys that share 22 bits.
+// The row is read twice (from L2 when it was just written) instead of four times, and everything after pass 2 works on ~1000 keys.
+// Bins that do not fit the list (heavy ties, rows beyond ~300 k elements with dense bins) take the four-pass path above.
+constexpr int Q_BINS = 2048;
+constexpr int Q_LIST_CAP = 8192;
+constexpr int Q_TINY_CAP = 1024;
+constexpr int Q_THREADS = 1024;
+
+// block-wide: bin of `hist[Q_BINS]` holding rank k; sh[0] = bin, sh[1] = count below, sh[2] = count in the bin, sh[5] = next
+// non-empty bin above it (Q_BINS if none).  wsum: 32 words of scratch.
+__device__ __forceinline__ void locate_block(const uint32_t* hist, uint32_t k, uint32_t* sh, uint32_t* wsum) {
+  constexpr int PER = Q_BINS / Q_THREADS;   // 2
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t c[PER], tot = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { c[j] = hist[tid * PER + j]; tot += c[j]; }
+  uint32_t incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  if (tid == 0) sh[5] = Q_BINS;
+  __syncthreads();
+  uint32_t wtot = wsum[lane], wincl = wtot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, o);
+    if (lane >= o) wincl += t;
+  }
+  const uint32_t excl = __shfl_sync(0xffffffffu, wincl - wtot, warp) + incl - tot;
+  if (k >= excl && k < excl + tot) {
+    uint32_t cum = excl;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      if (k < cum + c[j]) { sh[0] = tid * PER + j; sh[1] = cum; sh[2] = c[j]; break; }
+      cum += c[j];
+    }
+  }
+  __syncthreads();
+  const uint32_t sel = sh[0];
+  uint32_t nb = Q_BINS;
+#pragma unroll
+  for (int j = PER - 1; j >= 0; --j)
+    if (c[j] != 0 && (uint32_t)(tid * PER + j) > sel) nb = tid * PER + j;
+  nb = __reduce_min_sync(0xffffffffu, nb);
+  if (lane == 0 && nb < (uint32_t)Q_BINS) atomicMin(&sh[5], nb);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(Q_THREADS) quantile_rows_kernel(const float* __restrict__ u, int64_t B, int64_t n, int64_t stride,
+                                                                  uint32_t lo, uint32_t hi, float w, int lerp_fma,
+                                                                  float* __restrict__ thr_out, int32_t* __restrict__ rank_out,
+                                                                  float* __restrict__ val_out) {
+  __shared__ uint32_t hist[Q_BINS];
+  __shared__ uint32_t list[Q_LIST_CAP];
+  __shared__ uint32_t tiny[Q_TINY_CAP];
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t sh[16];   // [0..2],[5] locate; [3] nan; [4] smallest key above the selected bin; [6] list count; [7] tiny count; [8],[9] result; [10] smallest key of the list's next level-1 bin
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool need_next = hi > lo;
   for (int64_t row = blockIdx.x; row < B; row += gridDim.x) {
     const float* r = u + row * stride;
     const bool vec = ((reinterpret_cast<uintptr_t>(r) & 15) == 0) && ((n & 3) == 0);
-    RowSelectResult res;
-    select_row_exact(r, n, vec, lo, hi, hist, sh, res);
-    if (threadIdx.x == 0) {
-      float a = key_to_float(res.key_lo), b = key_to_float(res.key_hi);
+    for (int j = tid; j < Q_BINS; j += Q_THREADS) hist[j] = 0;
+    if (tid < 16) sh[tid] = (tid == 4 || tid == 10) ? 0xffffffffu : 0u;
+    __syncthreads();
+    // ---- pass 1: top 11 bits
+    uint32_t nan_seen = 0;
+    for_each_value(r, n, vec, [&](float f) {
+      nan_seen |= (f != f);
+      atomicAdd(&hist[float_to_key(f) >> 21], 1u);
+    });
+    if (__any_sync(0xffffffffu, nan_seen) && lane == 0) sh[3] = 1;
+    __syncthreads();
+    locate_block(hist, lo, sh, wsum);
+    const uint32_t d0 = sh[0], below0 = sh[1], cnt0 = sh[2];
+    const int has_nan = (int)sh[3];
+    uint32_t key_lo, key_hi;
+    __syncthreads();
+    if (cnt0 <= (uint32_t)Q_LIST_CAP) {
+      // ---- pass 2: compact the bin, smallest key above it
+      uint32_t best = 0xffffffffu;
+      for_each_value(r, n, vec, [&](float f) {
+        const uint32_t key = float_to_key(f);
+        const uint32_t bin = key >> 21;
+        if (bin == d0) list[atomicAdd(&sh[6], 1u)] = key;
+        else if (bin > d0) best = min(best, key);
+      });
+      best = __reduce_min_sync(0xffffffffu, best);
+      if (lane == 0 && best != 0xffffffffu) atomicMin(&sh[4], best);
+      for (int j = tid; j < Q_BINS; j += Q_THREADS) hist[j] = 0;
+      __syncthreads();
+      const uint32_t above_bin = sh[4];
+      // ---- level 1 over the list: bits 20..10
+      for (uint32_t j = tid; j < cnt0; j += Q_THREADS) atomicAdd(&hist[(list[j] >> 10) & (Q_BINS - 1)], 1u);
+      __syncthreads();
+      const uint32_t k1 = lo - below0;
+      locate_block(hist, k1, sh, wsum);
+      const uint32_t d1 = sh[0], below1 = sh[1], cnt1 = sh[2], next1 = sh[5];
+      const uint32_t k2 = k1 - below1;
+      const uint32_t prefix22 = (d0 << 11) | d1;
+      __syncthreads();
+      if (cnt1 <= (uint32_t)Q_TINY_CAP) {
+        const bool want_next_bin = need_next && (k2 + 1 >= cnt1) && next1 < (uint32_t)Q_BINS;
+        const uint32_t next22 = (d0 << 11) | next1;
+        uint32_t nbest = 0xffffffffu;
+        for (uint32_t j = tid; j < cnt0; j += Q_THREADS) {
+          const uint32_t key = list[j];
+          if ((key >> 10) == prefix22) tiny[atomicAdd(&sh[7], 1u)] = key;
+          else if (want_next_bin && (key >> 10) == next22) nbest = min(nbest, key);
+        }
+        if (want_next_bin) {
+          nbest = __reduce_min_sync(0xffffffffu, nbest);
+          if (lane == 0 && nbest != 0xffffffffu) atomicMin(&sh[10], nbest);
+        }
+        __syncthreads();
+        if (tid < 32) {
+          const uint32_t m = sh[7];
+          uint32_t klo, khi;
+          // successor outside the 22-bit group: smallest key of the next non-empty level-1 bin of the list, else of the row above bin d0
+          uint32_t outside = above_bin;
+          if (want_next_bin) outside = sh[10];
+          if (m <= 32u) {
+            const uint32_t mine = (lane < (int)m) ? tiny[lane] : 0xffffffffu;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < m; ++j) {
+              const uint32_t kj = __shfl_sync(0xffffffffu, mine, (int)j);
+              rank += (kj < mine || (kj == mine && j < (uint32_t)lane)) ? 1u : 0u;
+            }
+            const uint32_t is_lo = __ballot_sync(0xffffffffu, lane < (int)m && rank == k2);
+            const uint32_t is_hi = __ballot_sync(0xffffffffu, lane < (int)m && rank == k2 + 1u);
+            klo = __shfl_sync(0xffffffffu, mine, __ffs((int)is_lo) - 1);
+            khi = klo;
+            if (need_next) khi = is_hi ? __shfl_sync(0xffffffffu, mine, __ffs((int)is_hi) - 1) : outside;
+          } else {
+            uint32_t ans = 0;
+#pragma unroll 1
+            for (int bit = 9; bit >= 0; --bit) {
+              const uint32_t trial = (prefix22 << 10) | ans | (1u << bit);
+              uint32_t c = 0;
+              for (uint32_t j = lane; j < m; j += 32) c += (tiny[j] < trial);
+              c = __reduce_add_sync(0xffffffffu, c);
+              if (c <= k2) ans |= (1u << bit);
+            }
+            klo = (prefix22 << 10) | ans;
+            khi = klo;
+            if (need_next) {
+              uint32_t le = 0, above = 0xffffffffu;
+              for (uint32_t j = lane; j < m; j += 32) {
+                const uint32_t key = tiny[j];
+                le += (key <= klo);
+                if (key > klo) above = min(above, key);
+              }
+              le = __reduce_add_sync(0xffffffffu, le);
+              above = __reduce_min_sync(0xffffffffu, above);
+              if (k2 + 1 < le) khi = klo;
+              else if (above != 0xffffffffu) khi = above;
+              else khi = outside;
+            }
+          }
+          if (lane == 0) { sh[8] = klo; sh[9] = khi; }
+        }
+        __syncthreads();
+        key_lo = sh[8]; key_hi = sh[9];
+      } else {
+        RowSelectResult res;
+        select_row_exact(r, n, vec, lo, hi, hist, sh, res);   // heavy ties inside 22 bits: the four-pass path
+        key_lo = res.key_lo; key_hi = res.key_hi;
+      }
+    } else {
+      RowSelectResult res;
+      select_row_exact(r, n, vec, lo, hi, hist, sh, res);
+      key_lo = res.key_lo; key_hi = res.key_hi;
+    }
+    if (tid == 0) {
+      float a = key_to_float(key_lo), b = key_to_float(key_hi);
       float t = lerp_torch(a, b, w, lerp_fma);
-      if (res.has_nan) { t = __int_as_float(0x7fc00000); a = t; b = t; }
+      if (has_nan) { t = __int_as_float(0x7fc00000); a = t; b = t; }
       thr_out[row] = t;
       if (rank_out) { rank_out[2 * row] = (int32_t)lo; rank_out[2 * row + 1] = (int32_t)hi; }
       if (val_out) { val_out[2 * row] = a; val_out[2 * row + 1] = b; }
@@ -147,7 +315,7 @@ extern "C" int du_quantile_threshold(const float* u, int64_t B, int64_t n, int64
   uint32_t lo = (uint32_t)fl, hi = (uint32_t)ce;
   float w = rank - fl;
   unsigned grid = (unsigned)(B < 4096 ? B : 4096);
-  quantile_rows_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(u, B, n, stride, lo, hi, w, lerp_fma, thr_out, rank_out, val_out);
+  quantile_rows_kernel<<<grid, Q_THREADS, 0, (cudaStream_t)stream>>>(u, B, n, stride, lo, hi, w, lerp_fma, thr_out, rank_out, val_out);
   DU_LAUNCH_CHECK("quantile_rows_kernel");
   return DU_OK;
 }

@@ -338,15 +338,40 @@ struct ZStat { double s, ss; };
 
 __global__ void __launch_bounds__(256) znorm_partial_kernel(const void* u, int64_t stride, int dt, int64_t B, int64_t n,
                                                             double* partials /*[grid][2]*/, float pivot_hint) {
-  // pivot = first element of the tensor: keeps the squared sums small
+  // pivot = first element of the tensor: keeps the squared sums small.  Rows are walked as rows (no division per element); the
+  // per-thread sums run in fp32 over at most 64 values at a time before they are folded into the fp64 accumulators, so the
+  // loop costs two fp32 instructions per element instead of two fp64 ones (the partition into chunks is fixed: deterministic).
   const float pivot = load1(u, 0, dt);
   double s = 0.0, ss = 0.0;
-  const int64_t total = B * n;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
-    int64_t b = k / n, i = k - b * n;
-    double d = (double)load1(u, b * stride + i, dt) - (double)pivot;
-    s += d;
-    ss += d * d;
+  const bool vec = (n % 4 == 0) && (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(u) & (dt == DU_F32 ? 15 : 7)) == 0);
+  const int64_t groups = vec ? n / 4 : n;
+  // grid (x over the groups of a row, y over rows); four loads in flight per thread and trip
+  for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+    for (int64_t g0 = (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; g0 < groups; g0 += (int64_t)gridDim.x * blockDim.x * 4) {
+      float fs = 0.0f, fss = 0.0f;
+      if (vec) {
+        float v[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t g = g0 + (int64_t)j * blockDim.x;
+          if (g < groups) load4(u, b * stride + 4 * g, dt, v[j]);
+          else { v[j][0] = v[j][1] = v[j][2] = v[j][3] = pivot; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float d = v[j][e] - pivot; fs += d; fss = fmaf(d, d, fss); }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t g = g0 + (int64_t)j * blockDim.x;
+          if (g < groups) { const float d = load1(u, b * stride + g, dt) - pivot; fs += d; fss = fmaf(d, d, fss); }
+        }
+      }
+      s += (double)fs;
+      ss += (double)fss;
+    }
   }
   __shared__ double sh_s[8], sh_ss[8];
   for (int o = 16; o > 0; o >>= 1) {
@@ -359,8 +384,9 @@ __global__ void __launch_bounds__(256) znorm_partial_kernel(const void* u, int64
   if (threadIdx.x == 0) {
     double a = 0.0, c = 0.0;
     for (int j = 0; j < (int)(blockDim.x >> 5); ++j) { a += sh_s[j]; c += sh_ss[j]; }
-    partials[2 * blockIdx.x] = a;
-    partials[2 * blockIdx.x + 1] = c;
+    const int64_t blk = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    partials[2 * blk] = a;
+    partials[2 * blk + 1] = c;
   }
   (void)pivot_hint;
 }
@@ -423,23 +449,27 @@ extern "C" int du_tensor_threshold_mask(const void* u, int64_t u_stride, int u_d
   return launch_rows(B, n, vec, f, (cudaStream_t)stream);
 }
 
-static int znorm_blocks(int64_t total) {
-  int64_t blocks = (total + 256 * 8 - 1) / (256 * 8);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (blocks < 1) blocks = 1;
-  return (int)blocks;
+// grid of the partial-sum kernel: x over a row's groups (1024 per CTA and trip), y over rows, at most ~8 CTAs per SM in all
+static dim3 znorm_grid(int64_t B, int64_t n) {
+  int64_t gy = B < 1184 ? (B < 1 ? 1 : B) : 1184;
+  int64_t gx = (n / 4 + 1023) / 1024;
+  if (gx < 1) gx = 1;
+  const int64_t cap = (1184 + gy - 1) / gy;
+  if (gx > cap) gx = cap;
+  return dim3((unsigned)gx, (unsigned)gy);
 }
+static int znorm_blocks(int64_t B, int64_t n) { const dim3 g = znorm_grid(B, n); return (int)(g.x * g.y); }
 
-extern "C" size_t du_znorm_scratch_bytes(int64_t B, int64_t n) { return (size_t)znorm_blocks(B * n) * 2 * sizeof(double); }
+extern "C" size_t du_znorm_scratch_bytes(int64_t B, int64_t n) { return (size_t)znorm_blocks(B, n) * 2 * sizeof(double); }
 
 extern "C" int du_znorm_stats(const void* u, int64_t u_stride, int u_dtype, int64_t B, int64_t n, float* stats_out,
                               void* scratch, size_t scratch_bytes, du_stream_t stream) {
   du::DeviceGuard _dg;   // the device Python selected for this thread (du_set_device), restored on return
   if (!check_view(u, u_dtype) || !stats_out || !scratch || B <= 0 || n <= 0) return set_error(DU_ERR_BAD_ARG, "du_znorm_stats: bad arguments");
   if (scratch_bytes < du_znorm_scratch_bytes(B, n) || !aligned(scratch, 8)) return set_error(DU_ERR_SCRATCH, "du_znorm_stats: scratch too small or misaligned");
-  int blocks = znorm_blocks(B * n);
+  const int blocks = znorm_blocks(B, n);
   cudaStream_t st = (cudaStream_t)stream;
-  znorm_partial_kernel<<<blocks, 256, 0, st>>>(u, u_stride, u_dtype, B, n, (double*)scratch, 0.0f);
+  znorm_partial_kernel<<<znorm_grid(B, n), 256, 0, st>>>(u, u_stride, u_dtype, B, n, (double*)scratch, 0.0f);
   DU_LAUNCH_CHECK("znorm_partial_kernel");
   znorm_final_kernel<<<1, 32, 0, st>>>(u, u_dtype, (const double*)scratch, blocks, B * n, stats_out);
   DU_LAUNCH_CHECK("znorm_final_kernel");

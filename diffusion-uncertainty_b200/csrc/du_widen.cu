@@ -181,10 +181,19 @@ __global__ void __launch_bounds__(THREADS) row_sum_kernel(const void* x, int64_t
   const int64_t b = blockIdx.x;
   float acc = 0.0f;
   if (vec) {
-    for (int64_t g = threadIdx.x; g < n / 4; g += THREADS) {
-      float v[4];
-      load4(x, b * x_stride + 4 * g, dt, v);
-      acc += (v[0] + v[1]) + (v[2] + v[3]);
+    // four 16-byte loads in flight per thread (one CTA per row: the kernel lives on memory-level parallelism); the summation
+    // order is fixed by (thread, trip), so the result is deterministic
+    const int64_t n4 = n / 4;
+    for (int64_t g0 = threadIdx.x; g0 < n4; g0 += 4 * THREADS) {
+      float v[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t g = g0 + (int64_t)j * THREADS;
+        if (g < n4) load4(x, b * x_stride + 4 * g, dt, v[j]);
+        else { v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.0f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
     }
   } else {
     for (int64_t i = threadIdx.x; i < n; i += THREADS) acc += load1(x, b * x_stride + i, dt);

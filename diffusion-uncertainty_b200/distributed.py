@@ -80,6 +80,13 @@ class ShardedMoments:
         return m2, mean
 
     @staticmethod
+    def _scale(x, a):
+        if x.is_cuda:
+            from . import ops
+            return ops.scale(x, a)
+        return x * a          # (gloo tests of the host logic run on CPU tensors)
+
+    @staticmethod
     def _kernel_merge(means, m2s, counts, mode):
         from . import ops
         return ops.moments_merge(means, m2s, counts, mode=mode)
@@ -125,6 +132,13 @@ class ShardedMoments:
             count = n_local
         if self.world == 1:
             return self._merge([mean], [m2], [count], "centered" if mode == "centered" else "var")
+        if mode == "centered" and counts is not None:
+            # F1a needs no means: the partial sums of squared deviations about the COMMON centre add up — ONE all-reduce(sum) of N
+            # floats, then one scale by 1 / M.  (NCCL's sum order is fixed for a given communicator, so every
+            # rank holds the same bits.)
+            m2 = m2.float().contiguous()
+            dist.all_reduce(m2, op=dist.ReduceOp.SUM, group=self.group)
+            return self._scale(m2, 1.0 / float(sum(counts)))
         packed = torch.stack([mean.float(), m2.float()], dim=0).contiguous()          # [2, ...]
         gathered = torch.empty((self.world,) + tuple(packed.shape), device=packed.device, dtype=packed.dtype)
         dist.all_gather_into_tensor(gathered.view(self.world * packed.shape[0], *packed.shape[1:]), packed, group=self.group)

@@ -705,7 +705,7 @@ def _claim_philox(x: torch.Tensor, generator: Optional[torch.Generator]):
 
 
 def perturb_randn(x: torch.Tensor, a: float, b: float, generator: Optional[torch.Generator] = None, want_noise: bool = False,
-                  device_state: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None):
+                  device_state: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None, extra_offset: int = 0):
     """a*x + b*n, n = what `torch.randn_like(x)` would return now (bit-identical, generator advanced the same way), drawn in
     the kernel (du_perturb_randn): x read once, out written once, no noise tensor in HBM unless want_noise.
     device_state: int64[2] CUDA tensor {seed, offset} for draws replayed from a CUDA graph (see DeviceRng)."""
@@ -715,7 +715,7 @@ def perturb_randn(x: torch.Tensor, a: float, b: float, generator: Optional[torch
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
     noise = torch.empty_like(x) if want_noise else None
     if device_state is not None:
-        seed, offset, st_ptr = 0, 0, C.c_void_p(device_state.data_ptr())
+        seed, offset, st_ptr = 0, int(extra_offset), C.c_void_p(device_state.data_ptr())
     else:
         (seed, offset), st_ptr = _claim_philox(x, generator), None
     rc = L.load().du_perturb_randn(C.c_void_p(x.data_ptr()), _DT[x.dtype], x.numel(), seed, offset, st_ptr, float(a), float(b),
@@ -726,7 +726,8 @@ def perturb_randn(x: torch.Tensor, a: float, b: float, generator: Optional[torch
     return (out, noise) if want_noise else out
 
 
-def randn_like(x: torch.Tensor, generator: Optional[torch.Generator] = None, device_state: Optional[torch.Tensor] = None):
+def randn_like(x: torch.Tensor, generator: Optional[torch.Generator] = None, device_state: Optional[torch.Tensor] = None,
+               extra_offset: int = 0):
     """`torch.randn_like(x)` from du_perturb_randn's generator path alone (used by the tests and by DeviceRng)."""
     if not (x.is_cuda and x.dtype in _DT):
         raise RuntimeError("randn_like needs a CUDA tensor")
@@ -735,7 +736,7 @@ def randn_like(x: torch.Tensor, generator: Optional[torch.Generator] = None, dev
         return out
     _stream_ptr = _stream(x)
     if device_state is not None:
-        seed, offset, st_ptr = 0, 0, C.c_void_p(device_state.data_ptr())
+        seed, offset, st_ptr = 0, int(extra_offset), C.c_void_p(device_state.data_ptr())
     else:
         (seed, offset), st_ptr = _claim_philox(out, generator), None
     L.check(L.load().du_perturb_randn(None, _DT[x.dtype], out.numel(), seed, offset, st_ptr, 0.0, 0.0, None, _DT[x.dtype],
@@ -749,7 +750,10 @@ def perturb_fresh(x: torch.Tensor, a: float, b: float, noise_like: Optional[torc
     reproduced in the kernel (randn_fusable), else torch.randn_like followed by du_perturb.  Same values, same generator
     state afterwards, either way."""
     like = x if noise_like is None else noise_like
-    if like.shape == x.shape and like.dtype == x.dtype and like.device == x.device and randn_fusable(x):
+    same = like.shape == x.shape and like.dtype == x.dtype and like.device == x.device
+    if same and capture_rng is not None and x.is_cuda and x.is_contiguous() and torch.cuda.is_current_stream_capturing():
+        return capture_rng.perturb(x, a, b)        # inside a graph capture: the device-resident Philox state
+    if same and randn_fusable(x):
         return perturb_randn(x, a, b)
     noise = torch.randn_like(like)
     return perturb(x, noise if noise.shape == x.shape else noise.expand(x.shape), a, b)
@@ -757,20 +761,37 @@ def perturb_fresh(x: torch.Tensor, a: float, b: float, noise_like: Optional[torc
 
 class DeviceRng:
     """A Philox {seed, offset} pair in device memory, for perturbation draws inside a captured CUDA graph: every replay
-    continues the stream (du_rng_advance is part of the graph), and the values equal torch's for the same (seed, offset)."""
+    continues the stream (du_rng_advance is part of the graph), and the values equal torch's for the same (seed, offset).
 
-    def __init__(self, device, seed: int, offset: int = 0):
+    deferred=True: the draws of one graph pass their running increment as the extra offset and ONE `commit()` at the end of the
+    graph moves the state past all of them (a window step then costs one tiny launch for the RNG instead of one per draw)."""
+
+    def __init__(self, device, seed: int, offset: int = 0, deferred: bool = False):
         self.state = torch.tensor([seed, offset], dtype=torch.int64, device=device)
+        self.deferred = deferred
+        self._pending = 0
+
+    def _draw(self, fn, x, *a, **kw):
+        r = fn(x, *a, device_state=self.state, extra_offset=self._pending, **kw)
+        inc = randn_offset_increment(x.numel())
+        if self.deferred:
+            self._pending += inc
+        else:
+            self.advance(x.numel(), x)
+        return r
 
     def perturb(self, x: torch.Tensor, a: float, b: float, want_noise: bool = False):
-        r = perturb_randn(x, a, b, device_state=self.state, want_noise=want_noise)
-        self.advance(x.numel(), x)
-        return r
+        return self._draw(perturb_randn, x, a, b, want_noise=want_noise)
 
     def randn_like(self, x: torch.Tensor):
-        r = randn_like(x, device_state=self.state)
-        self.advance(x.numel(), x)
-        return r
+        return self._draw(randn_like, x)
+
+    def commit(self, like: torch.Tensor):
+        """deferred mode: advance the device state past every draw since the last commit (one launch)."""
+        if self._pending:
+            L.check(L.load().du_rng_advance(C.c_void_p(self.state.data_ptr()), self._pending, _stream(like)))
+            _count()
+            self._pending = 0
 
     def advance(self, numel: int, like: torch.Tensor):
         L.check(L.load().du_rng_advance(C.c_void_p(self.state.data_ptr()), randn_offset_increment(numel), _stream(like)))
@@ -778,6 +799,11 @@ class DeviceRng:
 
     def offset(self) -> int:
         return int(self.state[1].item())
+
+
+# A DeviceRng that perturb_fresh() uses for its draws while a CUDA graph is being captured (graphed.GraphedWindowStep sets it):
+# torch's own generator cannot be advanced by the host inside a capture, the device-resident state can.
+capture_rng: Optional[DeviceRng] = None
 
 
 def accumulate_slot(src: torch.Tensor, dst_slot: torch.Tensor):

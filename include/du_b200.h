@@ -247,8 +247,9 @@ int du_ema_update(const float* momentum, const void* u, int u_dtype, float beta,
  *         ATen/native/cuda/DistributionTemplates.h `normal_and_transform`), rounded to noise_dtype;
  *   out = a*x + b*n (one rounding per operation, as du_perturb).
  * x: N contiguous elements (NULL: only the noise is produced, into noise_out).  noise_out: nullable.
- * device_state: nullable device pointer to {seed, offset}; when given it overrides the host pair (draws that replay
- * from a CUDA graph: advance it in the same graph with du_rng_advance).
+ * device_state: nullable device pointer to {seed, offset}; when given its seed replaces the host seed and the host `offset` is
+ * ADDED to its offset (draws that replay from a CUDA graph: the k-th draw of a graph passes the increments of the draws before it
+ * as `offset`, and ONE du_rng_advance at the end of the graph moves the state past all of them).
  * Replaces `noise = torch.randn_like(pred_x_0)` + the expression of
  * SU/scheduling_ddim_uncertainty_zigzag_centered.py:529-538, SU/scheduling_ddim_uncertainty_centered.py:525-531,
  * uncertainty_guidance.py:86-88.  The caller advances its generator by du_randn_offset_increment(N).

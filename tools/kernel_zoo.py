@@ -31,10 +31,16 @@ def timeit(fn, reps=30):
         fn()
         torch.cuda.synchronize()
         return None
+    # `reps` launches captured in ONE CUDA graph: the wrappers' Python (5-40 us per call) is not what is being measured
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps * 1e3
@@ -74,7 +80,8 @@ def main():
     row("rows_kernel<DdimF>", "du_ddim_step(prev + x0)", timeit(lambda: ops.ddim_step(sb.eps, sb.sample, sb.coeffs)), 16 * n)
     # F7
     row("rows_kernel<PerturbF>", "du_perturb", timeit(lambda: ops.perturb(sb.sample, sb.eps, 0.99, 0.1)), 12 * n)
-    row("perturb_randn_kernel", "du_perturb_randn (noise drawn in the kernel)", timeit(lambda: ops.perturb_randn(sb.sample, 0.99, 0.1)), 8 * n,
+    rng = ops.DeviceRng(dev, 1234, 0, deferred=True)     # (a graph capture cannot advance torch's generator from the host)
+    row("perturb_randn_kernel", "du_perturb_randn (noise drawn in the kernel)", timeit(lambda: rng.perturb(sb.sample, 0.99, 0.1)), 8 * n,
         "Philox4x32-10 + Box-Muller per element, fixed by bit-parity with torch's generator")
     # F8 / N4
     row("rows_kernel<CopyF>", "du_accumulate_slot", timeit(lambda: ops.accumulate_slot(u, sb.maps[:, 5])), 8 * n)
