@@ -218,3 +218,38 @@ def test_guided_gradient_pipeline_call(ops):
     off, plain = run(1.0, 0.5), run(0.9, 0.0)
     assert torch.equal(off["gen_images"], plain["gen_images"])
     assert not torch.equal(a["gen_images"], plain["gen_images"])
+
+
+def test_threshold_fitting_on_disk_contract(tmp_path):
+    """N2 with the reference's file layout: scripts/compute_threshold_pixel_wise.py:86-116, 143-157 on the same files."""
+    import yaml
+    from diffusion_uncertainty_b200.threshold_fitting import fit_and_save_thresholds
+    g = torch.Generator().manual_seed(9)
+    folders = []
+    for k, n in enumerate((120, 150)):
+        d = tmp_path / f"run{k}"
+        d.mkdir()
+        torch.save(torch.rand(n, 3, 3, 8, 8, generator=g) ** 3, d / "uncertainty_0.pth")
+        torch.save(torch.rand(40, 3, 3, 8, 8, generator=g), d / "uncertainty_1.pth")        # < 100 samples: skipped
+        torch.save(torch.zeros(1, dtype=torch.uint8), d / "gen_images_0.pth")
+        (d / "args.yaml").write_text(yaml.safe_dump({"dataset": "imagenet64", "scheduler_type": "uncertainty_centered", "generation_steps": 50}))
+        folders.append(str(d))
+    perc = 0.9
+
+    def ref_fit(u):          # the reference's expressions, on the CPU
+        out = []
+        for i in range(u.shape[1]):
+            ut = u[:, i]
+            idx = ut.argsort(dim=0)[int(u.shape[0] * perc)].unsqueeze(0)
+            out.append(ut.gather(dim=0, index=idx).squeeze(0))
+        return torch.stack(out, dim=0)
+
+    for used in (folders[:1], folders):
+        paths = fit_and_save_thresholds(used, perc, str(tmp_path / "results"), extra_args={"on_cpu": False})
+        assert paths["thresholds"].endswith("results/thresholds/imagenet64/thresholds_uncertainty_centered_perc=0.9.pth")
+        got = torch.load(paths["thresholds"])
+        per_file = [ref_fit(torch.load(os.path.join(f, "uncertainty_0.pth")).half()).unsqueeze(0) for f in used]
+        want = per_file[0].squeeze(0) if len(per_file) == 1 else ref_fit(torch.cat(per_file, dim=0))
+        assert got.dtype == torch.float16 and got.shape == (3, 3, 8, 8) and torch.equal(got, want)
+        cfg = yaml.safe_load(open(paths["config"]))
+        assert cfg["dataset_config"]["generation_steps"] == 50 and cfg["perc"] == perc and cfg["dataset_folders"] == used
