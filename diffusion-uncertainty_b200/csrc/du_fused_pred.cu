@@ -734,8 +734,8 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
   const int64_t min_trips = (e_m && atoi(e_m) >= 4) ? atoi(e_m) : 6;
   // Launch shape.  The kernel keeps no copy of the map in shared memory, so it does not need the three-phase kernel's cluster
   // plan: ONE CTA of 1024 threads per image (no cluster barrier, no DSMEM, no wait for a peer CTA on a busier SM) is the
-  // fastest shape measured (ImageNet-128 step: 44.6 us against 47.4 us for clusters of two 512-thread CTAs), then 2 x 512, then
-  // the three-phase plan's shape.  DU_FUSED_CLUSTER / DU_FUSED_THREADS / DU_FUSED_PRED_THREADS pin it (tests, sweeps).
+  // fastest shape measured at batch 128 (ImageNet-128 step: 44.6 us against 47.4 us for clusters of two 512-thread CTAs).
+  // DU_FUSED_CLUSTER / DU_FUSED_THREADS / DU_FUSED_PRED_THREADS pin the shape (tests, sweeps).
   const char* e_c = getenv("DU_FUSED_CLUSTER");
   const char* e_t = getenv("DU_FUSED_THREADS");
   const char* e_pt = getenv("DU_FUSED_PRED_THREADS");
@@ -749,12 +749,25 @@ int launch_fused_pred(const FusedKParams& kp, const FusedPlan& plan, cudaStream_
     if (threads != 384 && threads != 512 && threads != 768 && threads != 1024) return 0;
     return try_pred(kp, plan.cluster, threads, min_trips, st);
   }
-  const int shapes[3][2] = {{1, 1024}, {2, 512}, {plan.cluster, plan.threads}};
-  for (int i = 0; i < 3; ++i) {
-    if (shapes[i][1] != 512 && shapes[i][1] != 1024) continue;
-    const int rc = try_pred(kp, shapes[i][0], shapes[i][1], min_trips, st);
+  // Few images (a batch sharded over the GPUs of a box: 64 / 32 / 16 images per GPU): one CTA per image would leave most of the
+  // 148 SMs idle, so the image is spread over a cluster of 2 / 4 / 8 CTAs of 512 threads — the smallest cluster that yields at
+  // least ~100 CTAs while every thread keeps min_trips row trips; if none does, the largest eligible cluster.
+  int tried = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int c = (pass == 0 ? 1 : 8); pass == 0 ? c <= 8 : c >= 1; c = (pass == 0 ? c * 2 : c / 2)) {
+      if (pass == 0 && p.B * c < 100) continue;
+      // (clusters of 8 with 3 trips per thread were measured too: 27.5 us against 19.6 us for 4 x 6 trips at 16 images — the
+      // 8-way DSMEM histogram sums cost more than the shorter streaming pass saves)
+      const int rc = try_pred(kp, c, c == 1 ? 1024 : 512, min_trips, st);
+      ++tried;
+      if (rc != 0) return rc;
+    }
+  }
+  if (plan.threads == 512 || plan.threads == 1024) {
+    const int rc = try_pred(kp, plan.cluster, plan.threads, min_trips, st);
     if (rc != 0) return rc;
   }
+  (void)tried;
   return 0;
 }
 

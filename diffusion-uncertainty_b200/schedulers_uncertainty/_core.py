@@ -269,6 +269,24 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
             prev = ops.perturb(prev, noise, 1.0, st.host["sigma"])
         st.prev, st.x0, st.eps = prev, x0, eps
 
+    def _restep_general(self, st: StepState, x0_source: torch.Tensor, eps_guided: torch.Tensor):
+        """The in-scheduler re-step in its general form (…uncertainty_threshold.py:554-574, …uncertainty_grad.py:551-570): x0 from
+        `x0_source` (the UNGUIDED model output) with clamp or dynamic thresholding, the guided score re-derived from the clipped x0
+        when use_clipped_model_output, x_(t-1) without the eta noise.  Separate launches; the one-launch du_guided_step covers
+        the configurations the reference's own configs use (no thresholding, score not re-derived)."""
+        h = st.host
+        c0 = ops.make_coeffs(h["sqrt_alpha_t"], h["sqrt_beta_t"], 0.0, 0.0, prediction_type="epsilon",
+                             clip_sample=bool(self.config.clip_sample) and not self.config.thresholding,
+                             clip_range=float(self.config.clip_sample_range))
+        x0 = ops.ddim_step(x0_source, st.sample, c0, want_prev=False, want_x0=True)[1]
+        if self.config.thresholding:
+            x0 = self._threshold_sample(x0)
+        eps = eps_guided
+        if st.use_clipped:
+            eps = ops.perturb(st.sample, x0, 1.0, -h["sqrt_alpha_t"])
+            eps = ops.scale(eps, 1.0 / h["sqrt_beta_t"])
+        st.prev, st.x0, st.eps = ops.perturb(x0, eps, h["sqrt_alpha_prev"], h["dir_coef"]), x0, eps
+
     def _threshold_sample(self, sample: torch.Tensor) -> torch.Tensor:
         """Imagen dynamic thresholding (…zigzag_centered.py:305-336): per-image quantile of |x0| by the radix-select
         kernel, then clamp / rescale."""

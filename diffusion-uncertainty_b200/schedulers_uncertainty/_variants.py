@@ -234,6 +234,10 @@ class ZNormThreshold(UncertaintyDDIMCore):
             ops.accumulate_slot(z, sink)
             z = sink
         # F4: the masked re-step; eta noise is NOT re-added (reference :566-571)
+        if self.config.thresholding:       # dynamic thresholding replaces the clamp of x0 (:557-558): the general re-step
+            guided = ops.guided_step(st.model_output, None, None, guidance="weights", mask=w, want_eps=True)["eps"]
+            self._restep_general(st, st.model_output, guided)
+            return z
         c = ops.make_coeffs(st.host["sqrt_alpha_t"], st.host["sqrt_beta_t"], st.host["sqrt_alpha_prev"], st.host["dir_coef"],
                             clip_sample=bool(self.config.clip_sample), clip_range=float(self.config.clip_sample_range),
                             use_clipped_model_output=st.use_clipped)
@@ -260,6 +264,18 @@ class Flip(UncertaintyDDIMCore):
     du_flip_h / du_flip_sqdiff (the flip back is folded into the difference kernel's addressing)."""
 
     channel_amax = False
+    host_copies = True     # the reference's flip scheduler returns x0, score (and, in the window, the map and pred_epsilon) as CPU
+                           # tensors (scheduling_ddim_flip.py:523-526); the sampling loops of this package switch the copies off
+
+    def _finish_output(self, out, st: StepState, window: bool):
+        if self.host_copies:
+            out.pred_original_sample = st.x0.cpu()
+            out.score = st.eps.cpu()
+            if window:
+                out.uncertainty = out.uncertainty.cpu()
+                out.pred_epsilon = st.eps.cpu()
+        else:
+            out.score = st.eps
 
     def _flip_map(self, st: StepState, out=None) -> torch.Tensor:
         flipped_output = self.predict_model(ops.flip_h(st.x0), st.t)
@@ -310,15 +326,18 @@ class UncertaintyGrad(UncertaintyDDIMCore):
             u.mean(dim=0).sum().backward()
         g = e.grad
         assert g is not None
-        c = ops.make_coeffs(h["sqrt_alpha_t"], h["sqrt_beta_t"], h["sqrt_alpha_prev"], h["dir_coef"],
-                            clip_sample=bool(self.config.clip_sample), clip_range=float(self.config.clip_sample_range),
-                            use_clipped_model_output=st.use_clipped)
-        r = ops.guided_step(st.eps, st.sample, c, guidance="grad_add", aux=g, lam=float(h["alpha_prod_t"]), x0_unguided=True,
-                            want_prev=True, want_x0=True, want_eps=True)
-        if self.config.prediction_type == "epsilon":
-            # x0 comes from model_output (:552); for epsilon prediction st.eps IS model_output
-            pass
-        st.prev, st.x0, st.eps = r["prev"], r["x0"], r["eps"]
+        if self.config.thresholding or st.eps is not st.model_output:
+            # x0 comes from model_output (:552) while the gradient is added to pred_epsilon — which differs from model_output once
+            # use_clipped_model_output re-derived it — and dynamic thresholding replaces the clamp: the general re-step
+            guided = ops.guided_step(st.eps, None, None, guidance="grad_add", aux=g, lam=float(h["alpha_prod_t"]), want_eps=True)["eps"]
+            self._restep_general(st, st.model_output, guided)
+        else:
+            c = ops.make_coeffs(h["sqrt_alpha_t"], h["sqrt_beta_t"], h["sqrt_alpha_prev"], h["dir_coef"],
+                                clip_sample=bool(self.config.clip_sample), clip_range=float(self.config.clip_sample_range),
+                                use_clipped_model_output=st.use_clipped)
+            r = ops.guided_step(st.eps, st.sample, c, guidance="grad_add", aux=g, lam=float(h["alpha_prod_t"]), x0_unguided=True,
+                                want_prev=True, want_x0=True, want_eps=True)
+            st.prev, st.x0, st.eps = r["prev"], r["x0"], r["eps"]
         u = u.detach()
         sink = self._map_out(u)
         if sink is not None:
