@@ -200,7 +200,7 @@ def step_config(workload, B_total, world, batch_sum, dtype_tag):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
-def eager_reference_step(eps, scores, sample, q, M, sc, batch_sum=True):
+def eager_reference_step(eps, scores, sample, q, M, sc, batch_sum=True, allreduce=None):
     """The reference's eager torch expressions of the step, on whatever device the tensors live on (no library of this
     repository involved): uncertainty_guidance.py:101-120 (F1c, F2a, F5) + SU/scheduling_ddim_uncertainty_zigzag_centered.py:
     472-510 (F3, epsilon prediction, clip_sample).  What a user of the reference runs on the same B200."""
@@ -211,7 +211,10 @@ def eager_reference_step(eps, scores, sample, q, M, sc, batch_sum=True):
     thr = torch.quantile(u.flatten(1).to(torch.float32), q, dim=1, keepdim=True).view(shp[0], *([1] * (len(shp) - 1)))
     mask = (u > thr).float()
     inv_var = 1 / u
-    post = (1 / (M * inv_var + 1 / sc["alpha_hat"])) * (inv_var * (pe.sum(dim=0) if batch_sum else pe))
+    S = pe.sum(dim=0) if batch_sum else pe
+    if batch_sum and allreduce is not None:      # batch sharded over ranks: the reference's sum runs over the WHOLE batch
+        allreduce(S)
+    post = (1 / (M * inv_var + 1 / sc["alpha_hat"])) * (inv_var * S)
     eg = pe * (1 - mask) + mask * post
     x0 = ((sample - sc["sqrt_beta_t"] * eg) / sc["sqrt_alpha_t"]).clamp(-1.0, 1.0)
     prev = sc["sqrt_alpha_prev"] * x0 + sc["dir_coef"] * eg
@@ -223,10 +226,14 @@ class StepBench:
     CUDA graphs of K steps, parity check and timings."""
     PREV_RING = 8     # x_{t-1} goes to a ring of buffers (8 x 25 MB at ImageNet-128): the 126 MB L2 cannot absorb the writes
 
-    def __init__(self, ops, workload, dtype_name, B, dev, seed, batch_sum=True, unfused=False):
+    def __init__(self, ops, workload, dtype_name, B, dev, seed, batch_sum=True, unfused=False, allreduce=None):
         self.ops, self.dev, self.workload, self.dtype_name = ops, dev, workload, dtype_name
         _, C, H, W, M, q = WORKLOADS[workload]
-        self.B, self.C, self.H, self.W, self.M, self.q, self.batch_sum = B, C, H, W, M, q, bool(batch_sum) and B > 1
+        # allreduce: a callable that sums a tensor over the ranks in place — given when the workload's batch is SHARDED over the
+        # ranks (strong scaling): the posterior's batch-axis sum then spans every rank's images (distributed.allreduce_batch_sum)
+        self.allreduce = allreduce
+        self.B, self.C, self.H, self.W, self.M, self.q = B, C, H, W, M, q
+        self.batch_sum = bool(batch_sum) and (B > 1 or allreduce is not None)
         self.dtype = DTYPES[dtype_name]
         self.sc = ddim_scalars()
         self.coeffs = ops.make_coeffs(self.sc["sqrt_alpha_t"], self.sc["sqrt_beta_t"], self.sc["sqrt_alpha_prev"], self.sc["dir_coef"],
@@ -255,6 +262,10 @@ class StepBench:
         if self.fused:
             self.plan.set_map_out(slot)
             self.plan.set_prev_out(self.prevs[i % self.PREV_RING])
+            if self.batch_sum and self.allreduce is not None:
+                ops.batch_sum(self.eps, out=self.S)      # this rank's images ...
+                self.allreduce(self.S)                   # ... summed over the ranks (NCCL all-reduce of one [C,H,W] row)
+                return self.plan.launch()["prev"]
             if self.batch_sum:                   # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
                 return self.plan.launch_with_batch_sum(self.eps, self.S)["prev"]      # du_batch_sum, then the step as its dependent launch
             return self.plan.launch()["prev"]
@@ -297,7 +308,8 @@ class StepBench:
         agree.  Returns a dict for the bench line; raises on failure."""
         prev = self.step(0)
         u_k = self.maps[:, 0]
-        u, thr, mask, prev_ref = eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum)
+        u, thr, mask, prev_ref = eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum,
+                                                      self.allreduce)
         torch.cuda.synchronize()
         # The bar for the map is the EXACT variance of the fp32 inputs (fp64 on the same device): within 1e-5 relative.  torch.var's
         # own fp32 result is reported next to it: on pixels whose variance is far below the typical one it deviates from the exact
@@ -346,7 +358,7 @@ class StepBench:
         for r in range(reps + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum)
+            eager_reference_step(self.eps, self.scores, self.sample, self.q, self.M, self.sc, self.batch_sum, self.allreduce)
             e1.record()
             torch.cuda.synchronize()
             if r > 0:
@@ -398,7 +410,14 @@ def run_ours(args):
     if scaling == "strong" and B_total % world != 0:
         raise SystemExit(f"--scaling strong needs the batch ({B_total}) to divide over {world} ranks")
     B = B_total // world if scaling == "strong" else B_total
-    sb_ = StepBench(ops, args.workload, args.dtype, B, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum, unfused=args.unfused)
+
+    def allreduce_sum(t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    # a batch sharded over the ranks shares ONE posterior sum: the step has an exchange (an all-reduce of the [C,H,W] row)
+    sharded = world > 1 and scaling == "strong" and bool(args.batch_sum)
+    sb_ = StepBench(ops, args.workload, args.dtype, B, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum, unfused=args.unfused,
+                    allreduce=allreduce_sum if sharded else None)
     fused = sb_.fused
 
     def barrier():
@@ -419,7 +438,7 @@ def run_ours(args):
     launches0 = ops.launch_count
     if use_graph:
         g_step, g_kernel = sb_.capture(step, args.steps), sb_.capture(kernel_only, args.steps)
-        n_step_launches = args.steps * (2 if sb_.batch_sum else 1)
+        n_step_launches = args.steps * (2 if sb_.batch_sum else 1)        # (library launches; the NCCL all-reduce is not counted)
         g_step.replay(); g_kernel.replay()            # one untimed replay each
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -526,7 +545,8 @@ def run_ours(args):
     other = None
     if world > 1 and not args.no_extras:
         oB = B_total if scaling == "strong" else B_total // world
-        ob = StepBench(ops, args.workload, args.dtype, oB, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum)
+        ob = StepBench(ops, args.workload, args.dtype, oB, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum,
+                       allreduce=allreduce_sum if (scaling == "weak" and bool(args.batch_sum)) else None)
         o_ms, o_k = ob.quick(args.steps)
         t = torch.tensor([o_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -548,7 +568,9 @@ def run_ours(args):
         dt_tag = {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype]
         cfg = step_config(args.workload, B * world, world, sb_.batch_sum, dt_tag)
         cfg.update({"images_per_gpu": B, "fused_single_launch": bool(fused),
-                    "parallelism": f"batch sharded x{world} ({B} images per GPU), no collective",
+                    "parallelism": (f"batch of {B * world} sharded x{world} ({B} images per GPU); one NCCL all-reduce(sum) of the posterior's "
+                                    f"batch-axis sum row ({C * H * W * 4 // 1024} KB) per step" if sharded else
+                                    f"{world} independent batches of {B} images, no collective"),
                     "prev_out": f"ring of {StepBench.PREV_RING} buffers ({StepBench.PREV_RING * n_el * 4 / 1e6:.0f} MB): x_(t-1) is written to HBM, not absorbed by L2",
                     "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
                           if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)})
@@ -602,6 +624,13 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     del out
     if world > 1:
+        # the graphs may hold captured NCCL kernels: release them (and drain the device) BEFORE the communicator goes away
+        if use_graph:
+            g_step = g_kernel = None
+        other = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
