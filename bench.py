@@ -9,8 +9,11 @@ metric is quoted on (226.5 MB of algorithmic traffic per step, 
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--dtype fp32|fp16|bf16]
 
-N>1 is launched by torchrun (one rank per GPU); the image batch is sharded by replication of the per-GPU
-batch (weak scaling, no data-path collective: moments are per element, quantiles per image).
+N>1 is launched by torchrun (one rank per GPU).  Default: the workload's batch is SHARDED over the ranks (strong scaling, BASELINE
+configs[2]; every shard a batch of its own, no data-path collective: moments are per element, quantiles per image), with the weak
+number (the whole batch on every GPU) as a sub-record; --scaling weak swaps the two, --allreduce-batch-sum makes the ranks share one
+posterior batch-axis sum (an NCCL all-reduce inside every step).  The default line also carries the ImageNet-128 sampling-loop img/s
+(BASELINE metric iii) as the `sampling_loop` sub-record.
 """
 import argparse
 import json
@@ -414,8 +417,11 @@ def run_ours(args):
     def allreduce_sum(t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
-    # a batch sharded over the ranks shares ONE posterior sum: the step has an exchange (an all-reduce of the [C,H,W] row)
-    sharded = world > 1 and scaling == "strong" and bool(args.batch_sum)
+    # Sharded batch: by default every rank treats its shard as a batch of its own — the reference's multi-GPU mode
+    # (scripts/generate_dataset_score_uncertainty_imagenet.py:51, 137-144: mp.spawn, one process per GPU, each with its own batches, so
+    # its `pred_epsilon.sum(dim=0)` runs over the process's batch) — and the step has no collective.  --allreduce-batch-sum makes the
+    # ranks share ONE posterior sum over the whole batch of 128 instead (an NCCL all-reduce of the [C,H,W] row inside every step).
+    sharded = world > 1 and scaling == "strong" and bool(args.batch_sum) and args.allreduce_batch_sum
     sb_ = StepBench(ops, args.workload, args.dtype, B, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum, unfused=args.unfused,
                     allreduce=allreduce_sum if sharded else None)
     fused = sb_.fused
@@ -446,7 +452,24 @@ def run_ours(args):
         # The K-step region lasts a few milliseconds, less than one nvidia-smi sampling period, so the sampler runs over a
         # sustained window of the SAME work: untimed replays before (until the first sample has arrived and the clocks have
         # ramped), the timed K steps, untimed replays after.  Throttle reasons seen anywhere in the window are reported.
+        # (with a collective inside the step every rank must run the SAME number of replays: the count for a given duration is agreed
+        # on once — slowest rank's replay time, all-reduced — instead of being timed per rank)
+        replay_s = [None]
+
         def sustain(seconds):
+            if sharded:
+                if replay_s[0] is None:
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    g_step.replay() if use_graph else [step(i) for i in range(args.steps)]
+                    torch.cuda.synchronize()
+                    t = torch.tensor([time.perf_counter() - t0], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    replay_s[0] = max(t.item(), 1e-5)
+                for _ in range(max(1, min(2000, int(seconds / replay_s[0])))):
+                    g_step.replay() if use_graph else [step(i) for i in range(args.steps)]
+                torch.cuda.synchronize()
+                return
             t_end = time.perf_counter() + seconds
             while time.perf_counter() < t_end:
                 if use_graph:
@@ -455,10 +478,14 @@ def run_ours(args):
                     for i in range(args.steps):
                         step(i)
                 torch.cuda.synchronize()
-        t_wait = time.perf_counter() + 3.0
-        while not clocks.rows and time.perf_counter() < t_wait:
-            sustain(0.05)
-        sustain(0.3)
+
+        if sharded:
+            sustain(0.6)       # (a fixed, rank-independent amount of work; the sampler has its first rows by then)
+        else:
+            t_wait = time.perf_counter() + 3.0
+            while not clocks.rows and time.perf_counter() < t_wait:
+                sustain(0.05)
+            sustain(0.3)
         barrier()
         # The ranks leave sustain() at different moments, so a GPU may have idled for tens of milliseconds at the barrier and
         # dropped its clocks: one untimed replay of the same K steps re-warms it, back to back with the timed one (no host
@@ -546,7 +573,7 @@ def run_ours(args):
     if world > 1 and not args.no_extras:
         oB = B_total if scaling == "strong" else B_total // world
         ob = StepBench(ops, args.workload, args.dtype, oB, dev, 1234 + rank + args.seed_offset, batch_sum=args.batch_sum,
-                       allreduce=allreduce_sum if (scaling == "weak" and bool(args.batch_sum)) else None)
+                       allreduce=allreduce_sum if (scaling == "weak" and bool(args.batch_sum) and args.allreduce_batch_sum) else None)
         o_ms, o_k = ob.quick(args.steps)
         t = torch.tensor([o_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -557,7 +584,10 @@ def run_ours(args):
     if args.with_loop and args.workload == "imagenet128_adm_b128_m5":
         del host_step
         torch.cuda.empty_cache()
-        loop = loop_record(args, "imagenet128_adm_loop", world, rank, local, dev, dist)
+        try:
+            loop = loop_record(args, "imagenet128_adm_loop", world, rank, local, dev, dist)
+        except Exception as ex:          # a sub-record must not take the headline line down
+            loop = {"error": repr(ex)[:300]} if rank == 0 else None
 
     if rank == 0:
         peak, peak_kind = peaks()
@@ -570,7 +600,9 @@ def run_ours(args):
         cfg.update({"images_per_gpu": B, "fused_single_launch": bool(fused),
                     "parallelism": (f"batch of {B * world} sharded x{world} ({B} images per GPU); one NCCL all-reduce(sum) of the posterior's "
                                     f"batch-axis sum row ({C * H * W * 4 // 1024} KB) per step" if sharded else
-                                    f"{world} independent batches of {B} images, no collective"),
+                                    (f"batch of {B * world} sharded x{world}: {B} images per GPU, each shard a batch of its own (the reference's "
+                                     "mp.spawn slicing), no collective" if scaling == "strong" and world > 1 else
+                                     f"{world} independent batches of {B} images, no collective")),
                     "prev_out": f"ring of {StepBench.PREV_RING} buffers ({StepBench.PREV_RING * n_el * 4 / 1e6:.0f} MB): x_(t-1) is written to HBM, not absorbed by L2",
                     "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
                           if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)})
@@ -599,10 +631,13 @@ def run_ours(args):
             line["sampling_loop"] = loop
         if world == 1 and not args.no_extras:
             # the reference's eager torch expressions on this GPU: the bar a user of the reference compares against
-            eg_ms = sb_.time_eager_reference()
-            line["gpu_eager_baseline"] = {"value": B * H * W / (eg_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": eg_ms,
-                                          "what": "the reference's eager torch expressions (stack / var / quantile / blend / DDIM) on the "
-                                                  "same GPU and tensors, CUDA events, best of 5", "speedup_of_value": eg_ms / ms_per_step}
+            try:
+                eg_ms = sb_.time_eager_reference()
+                line["gpu_eager_baseline"] = {"value": B * H * W / (eg_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": eg_ms,
+                                              "what": "the reference's eager torch expressions (stack / var / quantile / blend / DDIM) on the "
+                                                      "same GPU and tensors, CUDA events, best of 5", "speedup_of_value": eg_ms / ms_per_step}
+            except Exception as ex:      # informational legs must not take the headline line down
+                line["gpu_eager_baseline"] = {"error": repr(ex)[:200]}
             # the other BASELINE shapes and the autocast score dtype, same measurement in short form (parity-checked each)
             subs = {}
             for wl, dtn in ([(args.workload, "fp16")] if args.dtype == "fp32" else []) + [(w, "fp32") for w in WORKLOADS if w != args.workload]:
@@ -894,6 +929,8 @@ def main():
     ap.add_argument("--eager", action="store_true", help="time K eager launches from Python instead of one CUDA graph of K steps")
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
                     help="N > 1: strong = the workload's batch split over the ranks (default, BASELINE configs[2]); weak = the whole batch on every GPU")
+    ap.add_argument("--allreduce-batch-sum", action="store_true",
+                    help="N > 1, strong: one posterior batch-axis sum over ALL ranks' images (NCCL all-reduce of the [C,H,W] row in every step)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity check of the timed configuration")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (other scaling mode, other workloads, fp16, eager-torch GPU baseline)")
     ap.add_argument("--no-loop", dest="with_loop", action="store_false", help="skip the ImageNet-128 sampling-loop sub-record (img/s, ~1 min per loop at N=1)")

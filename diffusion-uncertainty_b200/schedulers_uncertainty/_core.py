@@ -368,24 +368,29 @@ class UncertaintyDDIMCore(ConfigurableScheduler):
         return sa, sb
 
     def add_noise(self, original_samples: torch.Tensor, noise: torch.Tensor, timesteps) -> torch.Tensor:
-        """sqrt(abar_t) x0 + sqrt(1-abar_t) n (…zigzag_centered.py:593-626).  A single timestep runs in du_perturb;
-        per-sample timestep vectors (training-style use, off the hot path) broadcast in torch."""
+        """sqrt(abar_t) x0 + sqrt(1-abar_t) n (…zigzag_centered.py:593-626).  One timestep: du_perturb (as a differentiable op when
+        the inputs are on an autograd graph — the gradient schedulers re-noise a traced x0); a vector of per-sample timesteps:
+        du_perturb_rows with the scalars read from device vectors."""
         sa, sb = self._per_sample_scalars(timesteps, original_samples)
-        traced = torch.is_grad_enabled() and (original_samples.requires_grad or noise.requires_grad)   # gradient schedulers
-        if sa.numel() == 1 and original_samples.is_cuda and not traced:
+        if not original_samples.is_cuda:
+            raise RuntimeError("add_noise: the uncertainty path has no CPU fallback, move the tensors to a CUDA device")
+        traced = torch.is_grad_enabled() and (original_samples.requires_grad or noise.requires_grad)
+        if sa.numel() == 1:
+            if traced:
+                return ops.perturb_autograd(original_samples, noise, float(sa), float(sb))
             return ops.perturb(original_samples, noise, float(sa), float(sb))
-        while sa.dim() < original_samples.dim():
-            sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)
-        return sa * original_samples + sb * noise
+        if traced:
+            raise RuntimeError("add_noise: per-sample timesteps are not differentiable here (no reference caller needs it)")
+        return ops.perturb_rows(original_samples, noise, sa, sb)
 
     def get_velocity(self, sample: torch.Tensor, noise: torch.Tensor, timesteps) -> torch.Tensor:
         """sqrt(abar_t) n - sqrt(1-abar_t) x (…zigzag_centered.py:629-646)."""
         sa, sb = self._per_sample_scalars(timesteps, sample)
-        if sa.numel() == 1 and sample.is_cuda:
+        if not sample.is_cuda:
+            raise RuntimeError("get_velocity: the uncertainty path has no CPU fallback, move the tensors to a CUDA device")
+        if sa.numel() == 1:
             return ops.perturb(noise, sample, float(sa), -float(sb))
-        while sa.dim() < sample.dim():
-            sa, sb = sa.unsqueeze(-1), sb.unsqueeze(-1)
-        return sa * noise - sb * sample
+        return ops.perturb_rows(noise, sample, sa, -sb)
 
     def __len__(self):
         return self.config.num_train_timesteps

@@ -252,3 +252,29 @@ def test_pixel_threshold_restatement_matches_reference_script(golden_dir):
     g = load(golden_dir, "pixel_thresholds")
     for perc in (0.15, 0.9):
         assert same(O.fit_pixel_thresholds(T(g["unc"]), perc).numpy(), g[f"thr_{perc}"])
+
+
+# ---- round 2: the pipeline classes, restated in oracle/du_oracle_pipelines.py, against fixtures recorded from the reference classes
+@pytest.mark.parametrize("tag", ["q", "t"])
+def test_oracle_posterior_pipeline_replays_the_reference(golden_dir, tag):
+    from oracle import du_oracle_pipelines as P
+    from tests.toy_models import ToyADM, seeded_noise
+    g = load(golden_dir, f"pipe_posterior_{tag}")
+    model = ToyADM(3, seed=51).eval()
+    thr = float(g["q"]) if tag == "q" else T(g["threshold"])
+    ac = torch.cumprod(1 - O.make_betas(), 0)
+    with seeded_noise(81):
+        imgs, last = P.posterior_pipeline(model, T(g["x_T"]), T(g["y"]), thr, batch_size=3, n_steps=8, start_step=2, num_steps=3, M=4, ac=ac)
+    assert same(last.numpy(), g["final_last_batch"]) and same(imgs.numpy(), g["gen_images"])
+
+
+def test_oracle_second_order_pipeline_replays_the_reference(golden_dir):
+    from oracle import du_oracle_pipelines as P
+    from tests.toy_models import ToyADM, seeded_noise
+    g = load(golden_dir, "pipe_second_order")
+    model = ToyADM(3, seed=52).eval()
+    ac = torch.cumprod(1 - O.make_betas(), 0)
+    with seeded_noise(82):
+        imgs, last = P.second_order_pipeline(model, T(g["x_T"]), T(g["y"]), float(g["q"]), batch_size=3, n_steps=8, start_step=2, num_steps=4,
+                                             M=4, ac=ac)
+    assert same(last.numpy(), g["final_last_batch"]) and same(imgs.numpy(), g["gen_images"])

@@ -253,3 +253,64 @@ def test_threshold_fitting_on_disk_contract(tmp_path):
         assert got.dtype == torch.float16 and got.shape == (3, 3, 8, 8) and torch.equal(got, want)
         cfg = yaml.safe_load(open(paths["config"]))
         assert cfg["dataset_config"]["generation_steps"] == 50 and cfg["perc"] == perc and cfg["dataset_folders"] == used
+
+
+# ---- round 2: the former eager-torch leftovers as kernels ------------------------------------------------------------------
+def test_second_order_blend_sign_add_is_bit_exact(ops):
+    """eps + u * sign(n) * mask (PU/..._guided_second_order.py:249), one du_guided_step launch, against the torch expression."""
+    g = torch.Generator().manual_seed(2)
+    eps, n = torch.randn(3, 3, 16, 16, generator=g), torch.randn(3, 3, 16, 16, generator=g)
+    u = torch.rand(3, 3, 16, 16, generator=g) ** 2
+    mask = (torch.rand(3, 3, 16, 16, generator=g) > 0.7).float()
+    n[0, 0, 0, 0] = 0.0
+    n[0, 0, 0, 1] = float("nan")
+    want = eps + u * torch.sign(n) * mask
+    got = ops.guided_step(eps.to(dev()), None, None, guidance="sign_add", u=u.to(dev()), mask=mask.to(dev()), aux=n.to(dev()), want_eps=True)["eps"]
+    assert bits_equal(got, want)
+
+
+def test_legacy_mul_blend_is_bit_exact(ops):
+    """eps (1 - m) + eps m g (generate_samples.py:953)."""
+    g = torch.Generator().manual_seed(3)
+    eps, grad = torch.randn(2, 3, 16, 16, generator=g), torch.randn(2, 3, 16, 16, generator=g)
+    mask = (torch.rand(2, 3, 16, 16, generator=g) > 0.5).float()
+    want = eps * (1 - mask) + eps * mask * grad
+    got = ops.guided_step(eps.to(dev()), None, None, guidance="mul_blend", mask=mask.to(dev()), aux=grad.to(dev()), want_eps=True)["eps"]
+    assert bits_equal(got, want)
+
+
+def test_std_map_and_its_backward(ops):
+    """pred_epsilons.std(dim=0) and d(std.mean(0).sum())/d scores (generate_samples.py:941-943) against torch autograd."""
+    g = torch.Generator().manual_seed(4)
+    scores = [torch.randn(2, 3, 8, 8, generator=g) for _ in range(5)]
+    ref = [s.clone().requires_grad_(True) for s in scores]
+    torch.stack(ref, 0).std(dim=0).mean(dim=0).sum().backward()
+    mine = [s.to(dev()).requires_grad_(True) for s in scores]
+    u = ops.moments_autograd(mine, "std")
+    u.mean(dim=0).sum().backward()
+    assert_close_rel(u.detach(), torch.stack(scores, 0).std(dim=0), 1e-5)
+    for a, b in zip(mine, ref):
+        assert_close_rel(a.grad, b.grad, 1e-4, atol=1e-7)
+
+
+def test_perturb_rows_and_per_sample_add_noise(ops):
+    """add_noise / get_velocity with a VECTOR of timesteps (SU/...zigzag_centered.py:606-646): one du_perturb_rows launch."""
+    from diffusion_uncertainty_b200.schedulers_uncertainty.scheduling_ddim import DDIMScheduler
+    g = torch.Generator().manual_seed(5)
+    x, nz = torch.randn(4, 3, 8, 8, generator=g), torch.randn(4, 3, 8, 8, generator=g)
+    t = torch.tensor([10, 500, 999, 0])
+    s = DDIMScheduler()
+    ac = s.alphas_cumprod
+    sa, sb = (ac[t] ** 0.5).view(-1, 1, 1, 1), ((1 - ac[t]) ** 0.5).view(-1, 1, 1, 1)
+    assert bits_equal(s.add_noise(x.to(dev()), nz.to(dev()), t.to(dev())), sa * x + sb * nz)
+    assert bits_equal(s.get_velocity(x.to(dev()), nz.to(dev()), t.to(dev())), sa * nz - sb * x)
+    assert bits_equal(ops.scale(x.to(dev()), 0.37), 0.37 * x)
+    # the differentiable forms used by the threshold-guided loops
+    e = x.to(dev()).requires_grad_(True)
+    x0 = ops.x0_autograd(e, nz.to(dev()), 0.8, 0.6)
+    out = ops.perturb_autograd(x0, nz.to(dev()), 0.8, 0.6)
+    out.sum().backward()
+    er = x.clone().requires_grad_(True)
+    (0.8 * ((nz - 0.6 * er) / 0.8) + 0.6 * nz).sum().backward()
+    assert bits_equal(x0.detach(), (nz - 0.6 * x) / 0.8)
+    assert_close_rel(e.grad, er.grad, 1e-6)
