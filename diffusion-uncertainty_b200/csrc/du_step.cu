@@ -118,8 +118,8 @@ __device__ __forceinline__ float guided_eps(int guidance, float eps, float m, fl
       return __fadd_rn(__fmul_rn(post_M, eps), __fmul_rn(lam, aux));
     case DU_GUIDE_MUL_BLEND:   // eps (1-m) + eps m g: generate_samples.py:953 (legacy percentile loop)
       return __fadd_rn(__fmul_rn(eps, __fsub_rn(1.0f, m)), __fmul_rn(__fmul_rn(eps, m), aux));
-    case DU_GUIDE_SIGN_ADD: {   // eps + u * sign(n) * m: PU/..._guided_second_order.py:249 (torch.sign: -1 / 0 / +1, NaN -> NaN)
-      const float sg = (aux > 0.0f) ? 1.0f : ((aux < 0.0f) ? -1.0f : ((aux == 0.0f) ? 0.0f : aux));
+    case DU_GUIDE_SIGN_ADD: {   // eps + u * sign(n) * m: PU/..._guided_second_order.py:249 (torch.sign = (0 < x) - (x < 0): NaN -> 0)
+      const float sg = (aux > 0.0f) ? 1.0f : ((aux < 0.0f) ? -1.0f : 0.0f);
       return __fadd_rn(eps, __fmul_rn(__fmul_rn(u, sg), m));
     }
     default:
