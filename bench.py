@@ -17,6 +17,7 @@ posterior batch-axis sum (an NCCL all-reduce inside every step).  The default li
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -41,6 +42,30 @@ DTYPES = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}
 T_UC = 10            # accumulation slots (num_steps_uc of the README command)
 TIMESTEP = 180       # first uncertainty timestep of `--start-step-uc 40` at 50 steps
 STEP_RATIO = 20
+
+
+L2_BYTES = 126e6
+IN_RING_MAX = 16
+
+
+def input_ring(alg_bytes):
+    """Timing rule: a step must not find its inputs in L2.  A working set above the 126 MB L2 needs nothing; a smaller one (the shards
+    of the strong split, the small workloads) rotates over this many resident copies of the input set, so that at least 2 x L2 of
+    other traffic passes between two uses of a copy (capped: below ~16 MB per step the numbers are L2-resident and latency-bound,
+    and the line says so)."""
+    if alg_bytes > L2_BYTES:
+        return 1
+    return min(IN_RING_MAX, int(math.ceil(2 * L2_BYTES / alg_bytes)) + 1)
+
+
+def l2_note(alg_bytes):
+    R, mb = input_ring(alg_bytes), alg_bytes / 1e6
+    if R == 1:
+        return "no flush: per-step working set %.1f MB per GPU > 126 MB L2" % mb
+    if (R - 1) * alg_bytes >= 2 * L2_BYTES:
+        return ("no flush: the steps rotate over %d resident copies of the input set (%.1f MB per step per GPU; %.0f MB pass between two "
+                "uses of a copy, > 2 x 126 MB L2) and over rings of output buffers" % (R, mb, (R - 1) * mb))
+    return "L2-resident, latency-bound: %.1f MB per step per GPU, %d input copies rotate (%.0f MB in all, < L2)" % (mb, R, R * mb)
 
 
 def peaks():
@@ -187,7 +212,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "uncertainty_step_throughput", "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": step_config(args.workload, B, world, True, "f32"),
+            "config": step_config(args.workload, B, world, True, "f32", "strong" if world > 1 else "weak"),
             "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port",
                              "sample": f"all {B} images of {args.workload} per step, {args.steps} steps, torch {torch.__version__} CPU, "
                                        f"{cores} threads"},
@@ -195,11 +220,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def step_config(workload, B_total, world, batch_sum, dtype_tag):
-    """`config` of a step line — the same keys and values in both arms."""
+def step_config(workload, B_total, world, batch_sum, dtype_tag, scaling="weak", allreduce=False):
+    """`config` of a step line — the same keys and values in both arms (--impl reference prints the GPU arm's configuration: it is a
+    function of the workload, the rank count and the scaling mode only; what is specific to one run sits in the line's `run`)."""
     _, C, H, W, M, q = WORKLOADS[workload]
-    return {"workload": workload, "global_batch": B_total, "shape": [C, H, W], "M": M, "q": q, "score_dtype": dtype_tag,
-            "chain": "F1c var(M+1) -> F2a quantile mask -> F5 posterior -> F3 DDIM (+F8 slot write)", "batch_sum": bool(batch_sum)}
+    sb = {"f32": 4, "f16": 2, "bf16": 2}[dtype_tag]
+    strong = scaling == "strong" and world > 1
+    B = B_total // world if strong else B_total
+    alg = algorithmic_bytes_per_element(M, sb) * B * C * H * W
+    if strong and allreduce:
+        par = (f"batch of {B_total} sharded x{world} ({B} images per GPU); one NCCL all-reduce(sum) of the posterior's batch-axis sum row "
+               f"({C * H * W * 4 // 1024} KB) per step")
+    elif strong:
+        par = (f"batch of {B_total} sharded x{world}: {B} images per GPU, each shard a batch of its own (the reference's mp.spawn slicing), "
+               "no collective")
+    else:
+        par = f"{world} independent batches of {B} images, no collective"
+    return {"workload": workload, "global_batch": B_total if strong else B_total * world, "shape": [C, H, W], "M": M, "q": q,
+            "score_dtype": dtype_tag, "chain": "F1c var(M+1) -> F2a quantile mask -> F5 posterior -> F3 DDIM (+F8 slot write)",
+            "batch_sum": bool(batch_sum), "images_per_gpu": B, "parallelism": par,
+            "l2": l2_note(alg)}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -229,7 +269,7 @@ class StepBench:
     CUDA graphs of K steps, parity check and timings."""
     PREV_RING = 8     # x_{t-1} goes to a ring of buffers (8 x 25 MB at ImageNet-128): the 126 MB L2 cannot absorb the writes
 
-    def __init__(self, ops, workload, dtype_name, B, dev, seed, batch_sum=True, unfused=False, allreduce=None):
+    def __init__(self, ops, workload, dtype_name, B, dev, seed, batch_sum=True, unfused=False, allreduce=None, in_ring=None):
         self.ops, self.dev, self.workload, self.dtype_name = ops, dev, workload, dtype_name
         _, C, H, W, M, q = WORKLOADS[workload]
         # allreduce: a callable that sums a tensor over the ranks in place — given when the workload's batch is SHARDED over the
@@ -249,12 +289,19 @@ class StepBench:
         self.prevs = [torch.empty(B, C, H, W, device=dev, dtype=torch.float32) for _ in range(self.PREV_RING)]
         self.n_el = B * C * H * W
         self.sb = 4 if self.dtype == torch.float32 else 2
+        # input sets the steps rotate over (input_ring): set 0 is the one above, the others are bit-identical copies of it
+        self.in_ring = input_ring(self.alg_bytes()) if in_ring is None else max(1, int(in_ring))
+        self.inputs = [(self.eps, self.scores, self.sample)]
+        for _ in range(self.in_ring - 1):
+            self.inputs.append((self.eps.clone(), [s.clone() for s in self.scores], self.sample.clone()))
         self.fused = (not unfused) and ops.fused_supported(C * H * W, self.dtype) > 0
-        self.plan = None
+        self.plan, self.plans = None, []
         if self.fused:
-            self.plan = ops.FusedStep(self.scores, self.eps, self.sample, q, self.coeffs, self.sc["alpha_hat"],
-                                      S=self.S if self.batch_sum else None, S_broadcast=self.batch_sum, map_out=self.maps[:, 0],
-                                      prev_out=self.prevs[0])
+            for eps_r, scores_r, sample_r in self.inputs:
+                self.plans.append(ops.FusedStep(scores_r, eps_r, sample_r, q, self.coeffs, self.sc["alpha_hat"],
+                                                S=self.S if self.batch_sum else None, S_broadcast=self.batch_sum,
+                                                map_out=self.maps[:, 0], prev_out=self.prevs[0]))
+            self.plan = self.plans[0]
         self.kernel = "moments_kernel"
 
     def alg_bytes(self):
@@ -262,33 +309,37 @@ class StepBench:
 
     def step(self, i):
         ops, slot = self.ops, self.maps[:, i % T_UC]
+        eps, scores, sample = self.inputs[i % self.in_ring]
         if self.fused:
-            self.plan.set_map_out(slot)
-            self.plan.set_prev_out(self.prevs[i % self.PREV_RING])
+            plan = self.plans[i % self.in_ring]
+            plan.set_map_out(slot)
+            plan.set_prev_out(self.prevs[i % self.PREV_RING])
             if self.batch_sum and self.allreduce is not None:
-                ops.batch_sum(self.eps, out=self.S)      # this rank's images ...
+                ops.batch_sum(eps, out=self.S)           # this rank's images ...
                 self.allreduce(self.S)                   # ... summed over the ranks (NCCL all-reduce of one [C,H,W] row)
-                return self.plan.launch()["prev"]
+                return plan.launch()["prev"]
             if self.batch_sum:                   # the reference's `pred_epsilon.sum(dim=0)` (uncertainty_guidance.py:119)
-                return self.plan.launch_with_batch_sum(self.eps, self.S)["prev"]      # du_batch_sum, then the step as its dependent launch
-            return self.plan.launch()["prev"]
+                return plan.launch_with_batch_sum(eps, self.S)["prev"]      # du_batch_sum, then the step as its dependent launch
+            return plan.launch()["prev"]
         if self.batch_sum:
-            ops.batch_sum(self.eps, out=self.S)
-        u = ops.moments(self.scores, center=self.eps, mode="var_with_center", out=slot)
+            ops.batch_sum(eps, out=self.S)
+        u = ops.moments(scores, center=eps, mode="var_with_center", out=slot)
         thr = ops.quantile_threshold(u, self.q)
-        r = ops.guided_step(self.eps, self.sample, self.coeffs, guidance="posterior", u=u, thr=thr,
-                            aux=self.S if self.batch_sum else self.eps, aux_broadcast=self.batch_sum, post_M=float(self.M),
+        r = ops.guided_step(eps, sample, self.coeffs, guidance="posterior", u=u, thr=thr,
+                            aux=self.S if self.batch_sum else eps, aux_broadcast=self.batch_sum, post_M=float(self.M),
                             inv_alpha_hat=1.0 / self.sc["alpha_hat"], want_eps=False)
         return r["prev"]
 
     def kernel_only(self, i):
         """the dominant kernel alone (roofline.achieved = its algorithmic bytes / its average launch duration)"""
         if self.fused:
-            self.plan.set_map_out(self.maps[:, i % T_UC])
-            self.plan.set_prev_out(self.prevs[i % self.PREV_RING])
-            self.plan.launch()
+            plan = self.plans[i % self.in_ring]
+            plan.set_map_out(self.maps[:, i % T_UC])
+            plan.set_prev_out(self.prevs[i % self.PREV_RING])
+            plan.launch()
         else:
-            self.ops.moments(self.scores, center=self.eps, mode="var_with_center", out=self.maps[:, i % T_UC])
+            eps, scores, _ = self.inputs[i % self.in_ring]
+            self.ops.moments(scores, center=eps, mode="var_with_center", out=self.maps[:, i % T_UC])
 
     def capture(self, fn, steps):
         g = torch.cuda.CUDAGraph()
@@ -578,7 +629,8 @@ def run_ours(args):
         t = torch.tensor([o_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         other = {"scaling": "weak" if scaling == "strong" else "strong", "images_per_gpu": oB, "ms_per_step": t.item(),
-                 "value": world * oB * H * W / (t.item() * 1e-3) / 1e6, "unit": "Mpix/s", "kernel": ob.kernel, "kernel_ms": o_k}
+                 "value": world * oB * H * W / (t.item() * 1e-3) / 1e6, "unit": "Mpix/s", "kernel": ob.kernel, "kernel_ms": o_k,
+                 "l2": l2_note(ob.alg_bytes())}
         del ob
     loop = None
     if args.with_loop and args.workload == "imagenet128_adm_b128_m5":
@@ -596,20 +648,13 @@ def run_ours(args):
         alg_kernel = alg_step if fused else ((M + 1) * sb + 4) * n_el
         achieved = alg_kernel / (k_ms * 1e-3) / 1e9
         dt_tag = {"fp32": "f32", "fp16": "f16", "bf16": "bf16"}[args.dtype]
-        cfg = step_config(args.workload, B * world, world, sb_.batch_sum, dt_tag)
-        cfg.update({"images_per_gpu": B, "fused_single_launch": bool(fused),
-                    "parallelism": (f"batch of {B * world} sharded x{world} ({B} images per GPU); one NCCL all-reduce(sum) of the posterior's "
-                                    f"batch-axis sum row ({C * H * W * 4 // 1024} KB) per step" if sharded else
-                                    (f"batch of {B * world} sharded x{world}: {B} images per GPU, each shard a batch of its own (the reference's "
-                                     "mp.spawn slicing), no collective" if scaling == "strong" and world > 1 else
-                                     f"{world} independent batches of {B} images, no collective")),
-                    "prev_out": f"ring of {StepBench.PREV_RING} buffers ({StepBench.PREV_RING * n_el * 4 / 1e6:.0f} MB): x_(t-1) is written to HBM, not absorbed by L2",
-                    "l2": "no flush: per-step working set %.1f MB > 126 MB L2" % (alg_step / 1e6)
-                          if alg_step > 126e6 else "working set fits L2 (%.1f MB): L2-resident numbers" % (alg_step / 1e6)})
+        cfg = step_config(args.workload, B_total, world, sb_.batch_sum, dt_tag, scaling, sharded)
+        run = {"fused_single_launch": bool(fused), "input_copies": sb_.in_ring,
+               "prev_out": f"ring of {StepBench.PREV_RING} buffers ({StepBench.PREV_RING * n_el * 4 / 1e6:.0f} MB): x_(t-1) is written to HBM, not absorbed by L2"}
         line = {
             "metric": "uncertainty_step_throughput", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
-            "vs_baseline": None, "dtype": dt_tag, "data": "synthetic", "config": cfg,
+            "vs_baseline": None, "dtype": dt_tag, "data": "synthetic", "config": cfg, "run": run,
             "parity_checked": parity is not None, "parity": parity,
             "step_hbm_frac": alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
             "step_algorithmic_GBps": alg_step / (ms_per_step * 1e-3) / 1e9,
@@ -649,7 +694,7 @@ def run_ours(args):
                     subs[f"{wl}:{dtn}"] = {"ms_per_step": s_ms, "kernel": x.kernel, "kernel_ms": kk_ms,
                                            "value": x.B * x.H * x.W / (s_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                                            "roofline_frac": x.alg_bytes() / (kk_ms * 1e-3) / 1e9 / peak, "parity_checked": True,
-                                           "mask_agreement": par["mask_agreement"]}
+                                           "mask_agreement": par["mask_agreement"], "l2": l2_note(x.alg_bytes())}
                     del x
                 except Exception as ex:   # a sub-record must not take the headline line down
                     subs[f"{wl}:{dtn}"] = {"error": repr(ex)[:200]}
