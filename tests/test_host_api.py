@@ -99,6 +99,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert json.loads(loop.strip().splitlines()[-1])["impl"] == "reference"
 
 
+def test_bench_config_is_the_same_dictionary_in_both_arms():
+    """the reference arm prints the GPU arm's `config` (workload, rank count and scaling mode decide it, nothing of the run does),
+    and every working set below the L2 size is rotated over enough copies of the input set or labelled L2-resident"""
+    import bench
+    for world in (1, 2, 4, 8):
+        scaling = "strong" if world > 1 else "weak"       # the defaults of both arms
+        ours = bench.step_config("imagenet128_adm_b128_m5", 128, world, 1, "f32", scaling, False)
+        ref = bench.step_config("imagenet128_adm_b128_m5", 128, world, True, "f32", scaling)
+        assert ours == ref and ours["global_batch"] == 128 and ours["images_per_gpu"] == 128 // world
+        assert ("no collective" in ours["parallelism"]) and ours["l2"].startswith("no flush")
+    weak = bench.step_config("imagenet128_adm_b128_m5", 128, 4, 1, "f32", "weak")
+    assert weak["global_batch"] == 512 and weak["images_per_gpu"] == 128
+    assert "all-reduce" in bench.step_config("imagenet128_adm_b128_m5", 128, 2, 1, "f32", "strong", True)["parallelism"]
+    for alg in (226.5e6, 113.2e6, 56.6e6, 28.3e6, 20e6):
+        R = bench.input_ring(alg)
+        assert R == 1 if alg > bench.L2_BYTES else (R - 1) * alg >= 2 * bench.L2_BYTES
+    assert bench.input_ring(1.3e6) == bench.IN_RING_MAX and bench.l2_note(1.3e6).startswith("L2-resident")
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "diffusion-uncertainty_b200")
     for dirpath, _, files in os.walk(pkg):
