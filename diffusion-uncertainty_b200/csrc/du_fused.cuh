@@ -210,9 +210,14 @@ __device__ __forceinline__ void hist_inc_if_eq(uint32_t hist_smem_addr, uint32_t
 // Only shared-memory histograms cross CTAs here.  They are complete in the owning SM's shared memory once the CTA
 // barrier in front has been passed, so the cluster barrier itself is relaxed: the release form costs a MEMBAR.ALL.GPU
 // (it waits for every outstanding global store of phase A).
+// (-DDU_CLUSTER_BARRIER_RELEASE builds the formally release / acquire form for A/B runs and tool checks.)
 __device__ __forceinline__ void cluster_barrier() {
   __syncthreads();
+#ifdef DU_CLUSTER_BARRIER_RELEASE
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
   asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
 }
 
 // ---- tensor memory (TMEM, 256 KB per SM, otherwise idle in this tensor-core-free kernel) as a per-thread stash: phase A
