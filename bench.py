@@ -76,12 +76,17 @@ def peaks():
         return 6650.0, "fallback"
 
 
-def ncu_traffic(kernel):
+def ncu_traffic(kernel, workload=None, images_per_gpu=None, dtype=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full` summary of this
-    round (profiles/ncu_traffic.json; written by tools/ncu_summary.py from the capture).  None when there is no capture."""
+    round (profiles/ncu_traffic.json; written by tools/ncu_summary.py from the capture).  None when there is no capture of this
+    kernel at this workload, per-GPU batch and score dtype."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+            rec = json.load(f).get(kernel, {})
+        for key, have in (("workload", workload), ("images_per_gpu", images_per_gpu), ("score_dtype", dtype)):
+            if have is not None and rec.get(key) is not None and rec[key] != have:
+                return None
+        return rec.get("dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -659,7 +664,7 @@ def run_ours(args):
             "step_hbm_frac": alg_step / (ms_per_step * 1e-3) / 1e9 / peak,
             "step_algorithmic_GBps": alg_step / (ms_per_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": ncu_traffic(dominant),
+                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": ncu_traffic(dominant, args.workload, B, args.dtype),
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_kernel,
                          "timing": "CUDA events around %d back-to-back launches%s" % (args.steps, " replayed from one CUDA graph" if use_graph else "")},
             "ms_per_step_by_rank": [m / args.steps for m in ms_ranks],
