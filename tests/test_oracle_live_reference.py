@@ -1,0 +1,169 @@
+"""The oracle against the LIVE reference, where the reference is present (the build container: /root/reference, read-only, imported
+with the diffusers base-class stand-in of tests/golden/_standin).  The committed fixtures pin the oracle at a handful of recorded
+configurations; here the same comparison runs on configurations and seeds that are NOT in the fixtures — other step counts,
+windows, M, zig-zag counts, eta, beta schedules, batch shapes — bit for bit on the CPU.  Skipped on the GPU box (no reference there);
+nothing under `-m gpu`, smoke() or bench.py depends on this file."""
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import du_oracle as O
+from tests.helpers import l4_sampling_loop
+from tests.toy_models import ToyADM, seeded_noise
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "diffusion_uncertainty")),
+                                reason="the reference tree is only present in the build container")
+SU = "diffusion_uncertainty.schedulers_uncertainty."
+
+
+@pytest.fixture(scope="module")
+def reference_on_path():
+    added = [os.path.join(HERE, "golden", "_standin"), REF]
+    for p in added:
+        sys.path.insert(0, p)
+    yield
+    for p in added:
+        sys.path.remove(p)
+    for name in [m for m in sys.modules if m == "diffusers" or m.startswith("diffusers.") or m.startswith("diffusion_uncertainty.")
+                 or m == "diffusion_uncertainty"]:
+        del sys.modules[name]
+
+
+def base_config(**over):
+    cfg = dict(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear", clip_sample=True,
+               set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", timestep_spacing="leading")
+    cfg.update(over)
+    return cfg
+
+
+def bits_equal(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if a.dtype == torch.float32:
+        # NaNs in the same places, everything else bit for bit (the sign of a zero included)
+        return bool(torch.equal(torch.isnan(a), torch.isnan(b))) and \
+            bool(torch.equal(a.nan_to_num(0.0).view(torch.int32), b.nan_to_num(0.0).view(torch.int32)))
+    return bool(torch.equal(a, b))
+
+
+# variant (oracle name), reference module, class, ctor kwargs, n_steps, seed, eta, dropout, config overrides, (B, H)
+LIVE_CASES = [
+    ("zigzag_centered", "scheduling_ddim_uncertainty_zigzag_centered", dict(M=2, after_step=3, num_steps_uc=6, num_zigzag=4), 12, 101, 0.0,
+     False, {}, (3, 8)),
+    ("zigzag_centered", "scheduling_ddim_uncertainty_zigzag_centered", dict(M=7, after_step=0, num_steps_uc=3, num_zigzag=1), 10, 102, 0.7,
+     False, dict(beta_schedule="scaled_linear", beta_start=0.00085, beta_end=0.012, clip_sample=False, set_alpha_to_one=False, steps_offset=1),
+     (2, 12)),
+    ("zigzag", "scheduling_ddim_uncertainty_zigzag", dict(M=3, after_step=2, num_steps_uc=4, num_zigzag=3), 10, 103, 0.0, False,
+     dict(beta_schedule="squaredcos_cap_v2"), (5, 8)),
+    ("centered", "scheduling_ddim_uncertainty_centered", dict(M=2, after_step=6, num_steps_uc=3, predict_next=False), 15, 104, 0.2, False, {},
+     (2, 8)),
+    ("centered", "scheduling_ddim_uncertainty_centered", dict(M=4, after_step=1, num_steps_uc=8, predict_next=True), 10, 105, 0.0, False,
+     dict(clip_sample=False), (3, 8)),
+    ("infer_noise", "scheduling_ddim_infer_noise", dict(M=3, after_step=4, num_steps_uc=4, predict_next=True), 12, 106, 0.0, False, {}, (2, 8)),
+    ("mc_dropout", "scheduling_ddim_mc_dropout", dict(M=3, after_step=2, num_steps_uc=5), 10, 107, 0.0, True, {}, (4, 8)),
+    ("threshold", "scheduling_ddim_uncertainty_threshold",
+     dict(M=3, after_step=2, num_steps_uc=5, uncertainty_threshold=0.2, uncertainty_threshold_mode="max"), 10, 108, 0.0, False, {}, (3, 8)),
+    ("threshold", "scheduling_ddim_uncertainty_threshold",
+     dict(M=4, after_step=3, num_steps_uc=4, uncertainty_threshold=-0.3, uncertainty_threshold_mode="min"), 10, 109, 0.0, False, {}, (2, 12)),
+    ("multiscale", "scheduling_ddim_infer_noise_multiscale_threshold", dict(M=4, after_step=2, num_steps_uc=6), 12, 110, 0.0, False, {}, (3, 8)),
+    ("flip_threshold", "scheduling_ddim_flip_threshold",
+     dict(M=1, after_step=2, num_steps_uc=6, uncertainty_threshold=0.0, uncertainty_threshold_mode="min"), 12, 111, 0.0, False, {}, (3, 8)),
+    ("uncertainty_grad", "scheduling_ddim_uncertainty_grad", dict(M=2, after_step=3, num_steps_uc=3, predict_next=False), 10, 112, 0.0, False, {},
+     (2, 8)),
+    ("mc_dropout_gradient", "scheduling_ddim_mc_dropout_gradient", dict(M=3, after_step=1, num_steps_uc=4), 8, 113, 0.0, True, {}, (2, 8)),
+]
+
+
+@pytest.mark.parametrize("case", LIVE_CASES, ids=[f"{c[0]}-{c[5]}" for c in LIVE_CASES])
+def test_oracle_scheduler_equals_live_reference(reference_on_path, case):
+    variant, module, kw, n_steps, seed, eta, dropout, cfg, (B, H) = case
+    g = torch.Generator().manual_seed(500 + seed)
+    x_T = torch.randn(B, 3, H, H, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+
+    def reference():
+        model = ToyADM(3, seed=seed, dropout=dropout).eval()
+        cls = getattr(importlib.import_module(SU + module), "DDIMSchedulerUncertaintyImagenetClassConditioned")
+        with contextlib.redirect_stdout(io.StringIO()):
+            sched = cls.from_config(base_config(**cfg), unet=model, **kw)
+            sched.set_timesteps(n_steps)
+            with seeded_noise(2000 + seed):
+                return sched, l4_sampling_loop(sched, model, x_T, y, eta=eta)
+
+    def oracle():
+        model = ToyADM(3, seed=seed, dropout=dropout).eval()
+        sched = O.OracleScheduler(variant, None, unet=model, **kw, **cfg)
+        sched.predict = lambda x, t: model(x, t, y=sched.prompt_embeds)[:, :3]
+        sched.set_timesteps(n_steps)
+        with seeded_noise(2000 + seed):
+            return sched, l4_sampling_loop(sched, model, x_T, y, eta=eta)
+
+    rs, r = reference()
+    os_, o = oracle()
+    assert torch.equal(rs.timesteps, os_.timesteps)
+    assert int(rs.timestep_after_step) == int(os_.timestep_after_step) and int(rs.timestep_end_step) == int(os_.timestep_end_step)
+    assert r["uncertainty"].shape[1] > 0, "the case must have a window"
+    for key in ("uncertainty", "score", "final"):
+        assert bits_equal(r[key], o[key]), key
+    assert len(r["prevs"]) == len(o["prevs"]) and all(bits_equal(a, b) for a, b in zip(r["prevs"], o["prevs"]))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_threshold_map_equals_live_reference(reference_on_path, seed):
+    """calculate_threshold_map (PU/...posterior_distribution.py:10-30): scalar percentile (both threshold types, ties, a NaN row,
+    ranks >= 2 incl. the [B, L, C] layout) and the tensor-threshold branch"""
+    mod = importlib.import_module("diffusion_uncertainty.pipeline_uncertainty."
+                                  "pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution")
+    g = torch.Generator().manual_seed(900 + seed)
+    shapes = [(3, 3, 8, 8), (2, 4, 16, 16), (5, 7), (2, 33, 6), (1, 4, 64, 64), (4, 1, 5, 9)]
+    shape = shapes[seed % len(shapes)]
+    u = torch.rand(shape, generator=g) ** 3
+    if seed % 2:
+        u = (u * 8).round() / 8               # heavy ties
+    if seed == 3:
+        u[0].view(-1)[1] = float("nan")       # NaN row -> NaN threshold -> all-false mask
+    for q in (0.05, 0.5, 0.9, 0.99):
+        for kind in ("higher", "lower"):
+            assert bits_equal(mod.calculate_threshold_map(q, None, u, kind), O.calculate_threshold_map(q, None, u, kind)), (q, kind)
+    if len(shape) == 4:
+        thr = torch.rand((4,) + shape[1:], generator=g).half()
+        for i in (0, 3):
+            for kind in ("higher", "lower"):
+                assert bits_equal(mod.calculate_threshold_map(thr, i, u, kind), O.calculate_threshold_map(thr, i, u, kind))
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_posterior_update_equals_live_reference(reference_on_path, seed):
+    """estimate_score_update_posterior (PU/...posterior_distribution.py:32-68: F7 re-noising, M forwards, F1c, F5 with the batch-axis
+    sum of the LAST perturbed prediction) on random shapes, M and alpha_hat — against the oracle's restatement of the same lines"""
+    from oracle import du_oracle_pipelines as P
+    mod = importlib.import_module("diffusion_uncertainty.pipeline_uncertainty."
+                                  "pipeline_sampler_class_conditional_uncertainty_guided_posterior_distribution")
+    g = torch.Generator().manual_seed(700 + seed)
+    B, H = [(2, 8), (4, 16), (1, 8), (3, 4)][seed]
+    M = [2, 5, 16, 3][seed]
+    t = [900, 500, 180, 20][seed]
+    model = ToyADM(3, seed=40 + seed).eval()
+    x = torch.randn(B, 3, H, H, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+    t_tensor = torch.full((B,), t, dtype=torch.long)
+    ac = torch.cumprod(1.0 - O.make_betas(), dim=0)
+    a = ac[[3, 20, 41, 49][seed]]                    # the pipeline indexes alphas_cumprod by the STEP number (:151)
+    with torch.no_grad():
+        eps = model(x, t_tensor, y=y)[:, :3]
+        with seeded_noise(3000 + seed):
+            u_r, post_r = mod.estimate_score_update_posterior(M, model, None, x, y, t_tensor, eps, x, a)
+        with seeded_noise(3000 + seed):
+            preds = P.perturbed_predictions(lambda z: model(z, t_tensor, y=y)[:, :3], x, eps, x, a, M)
+        u_o = O.variance_with_center(preds, eps)
+        post_o = O.posterior_blend(eps, u_o, torch.ones_like(u_o), M, a, sum_source=preds[-1], batch_sum=True)
+    assert bits_equal(u_r, u_o)
+    assert bits_equal(post_r, post_o)
