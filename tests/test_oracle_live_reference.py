@@ -167,3 +167,87 @@ def test_oracle_posterior_update_equals_live_reference(reference_on_path, seed):
         post_o = O.posterior_blend(eps, u_o, torch.ones_like(u_o), M, a, sum_source=preds[-1], batch_sum=True)
     assert bits_equal(u_r, u_o)
     assert bits_equal(post_r, post_o)
+
+
+class _Recorder:
+    """keeps the last x_{t-1} of a wrapped scheduler.step and rewinds the seeded generator after every step (the plain scheduler the
+    pipelines are driven with draws nothing; the reference's uncertainty scheduler, used here with an empty window, draws every step)"""
+
+    def __init__(self, sched, gen):
+        self.gen, self.inner, self.last = gen, sched.step, None
+        sched.step = self
+
+    def __call__(self, *a, **kw):
+        state = self.gen.get_state()
+        out = self.inner(*a, **kw)
+        self.gen.set_state(state)
+        self.last = out.prev_sample.detach().clone()
+        return out
+
+
+def _plain_reference_ddim(n_steps):
+    """the reference's own DDIM arithmetic as a plain scheduler: its centred uncertainty scheduler with an EMPTY window"""
+    mod = importlib.import_module(SU + "scheduling_ddim_uncertainty_centered")
+
+    class DDIMScheduler(mod.DDIMSchedulerUncertainty):
+        def set_timesteps(self, n, device=None):
+            self.config.after_step, self.config.num_steps_uc = 0, 1
+            super().set_timesteps(n, device)
+            self.timestep_after_step, self.timestep_end_step = -1, 10 ** 9
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        sched = DDIMScheduler.from_config(base_config(), unet=None, M=1)
+        sched.set_timesteps(n_steps)
+    return sched
+
+
+# kind, N images, batch size, n_steps, start_step, num_steps, M, threshold (float percentile or "tensor"), seed
+PIPE_CASES = [
+    ("posterior", 4, 4, 10, 0, 2, 2, 0.5, 201),
+    ("posterior", 7, 3, 5, 1, 3, 6, 0.95, 202),        # ragged last batch; window reaching the last step (`start + num >= i`)
+    ("posterior", 3, 2, 10, 4, 1, 3, "tensor", 203),
+    ("second_order", 4, 4, 10, 0, 3, 2, 0.5, 204),
+    ("second_order", 5, 2, 5, 2, 5, 5, 0.99, 205),     # ragged last batch; window longer than the loop
+    ("second_order", 3, 3, 10, 3, 2, 3, "tensor", 206),
+]
+
+
+@pytest.mark.parametrize("case", PIPE_CASES, ids=[f"{c[0]}-{c[-1]}" for c in PIPE_CASES])
+def test_oracle_pipeline_equals_live_reference(reference_on_path, case):
+    """DiffusionClassConditionalGuidedPosteriorDistribution / ...GuidedSecondOrder.__call__ (PU/...posterior_distribution.py:117-188,
+    PU/...second_order.py:110-194) against oracle/du_oracle_pipelines.py, bit for bit.  The posterior class calls the four-argument
+    module function with three arguments (:159): the missing threshold_type is supplied, nothing else is changed."""
+    from oracle import du_oracle_pipelines as P
+    kind, N, bs, n_steps, start, num, M, thr, seed = case
+    name = "pipeline_sampler_class_conditional_uncertainty_guided_" + ("posterior_distribution" if kind == "posterior" else "second_order")
+    mod = importlib.import_module("diffusion_uncertainty.pipeline_uncertainty." + name)
+    g = torch.Generator().manual_seed(seed)
+    x_T = torch.randn(N, 3, 8, 8, generator=g)
+    y = torch.randint(0, 10, (N,), generator=g)
+    if thr == "tensor":
+        thr = torch.rand(n_steps, 3, 8, 8, generator=g) * (2e-3 if kind == "posterior" else 1e-3)
+    cpu = torch.device("cpu")
+    ac = torch.cumprod(1 - O.make_betas(), 0)
+
+    model = ToyADM(3, seed=seed).eval()
+    sched = _plain_reference_ddim(n_steps)
+    orig = mod.calculate_threshold_map
+    if kind == "posterior":
+        mod.calculate_threshold_map = lambda t, i, u, threshold_type="higher": orig(t, i, u, threshold_type)
+    try:
+        if kind == "posterior":
+            pipe = mod.DiffusionClassConditionalGuidedPosteriorDistribution(model, sched, thr, 8, cpu, bs, 0, M=M)
+        else:
+            pipe = mod.DiffusionClassConditionalGuidedSecondOrder(model, sched, thr, 8, cpu, bs, 0, M=M, threshold_type="higher")
+        with seeded_noise(4000 + seed) as gen, contextlib.redirect_stdout(io.StringIO()):
+            rec = _Recorder(sched, gen)
+            res = pipe(X_T=x_T, y=y, start_step=start, num_steps=num)
+    finally:
+        mod.calculate_threshold_map = orig
+
+    model = ToyADM(3, seed=seed).eval()
+    fn = P.posterior_pipeline if kind == "posterior" else P.second_order_pipeline
+    with seeded_noise(4000 + seed):
+        imgs, last = fn(model, x_T, y, thr, batch_size=bs, n_steps=n_steps, start_step=start, num_steps=num, M=M, ac=ac)
+    assert bits_equal(rec.last, last)
+    assert bits_equal(res["gen_images"], imgs)
