@@ -251,3 +251,80 @@ def test_oracle_pipeline_equals_live_reference(reference_on_path, case):
         imgs, last = fn(model, x_T, y, thr, batch_size=bs, n_steps=n_steps, start_step=start, num_steps=num, M=M, ac=ac)
     assert bits_equal(rec.last, last)
     assert bits_equal(res["gen_images"], imgs)
+
+
+DPM_LIVE_CASES = [
+    # ctor kwargs, n_steps, seed, config overrides, (B, H)
+    (dict(M=2, after_step=1, num_steps_uc=6), 9, 301, dict(variance_type="fixed_small"), (3, 8)),
+    (dict(M=5, after_step=0, num_steps_uc=2, solver_type="heun"), 6, 302,
+     dict(variance_type="fixed_small", beta_schedule="scaled_linear", timestep_spacing="trailing"), (2, 12)),
+    (dict(M=3, after_step=3, num_steps_uc=3, solver_order=1, final_sigmas_type="sigma_min"), 10, 303,
+     dict(variance_type="learned_range", timestep_spacing="linspace"), (4, 8)),
+]
+
+
+@pytest.mark.parametrize("case", DPM_LIVE_CASES, ids=[str(c[2]) for c in DPM_LIVE_CASES])
+def test_oracle_dpm2_scheduler_equals_live_reference(reference_on_path, case):
+    """SU/scheduling_dpm_2_uncertainty_centered.py (DPM-Solver++ multistep with the centred map) against oracle/du_oracle_dpm.py"""
+    from oracle.du_oracle_dpm import OracleDPM2Scheduler
+    kw, n_steps, seed, cfg, (B, H) = case
+    g = torch.Generator().manual_seed(500 + seed)
+    x_T = torch.randn(B, 3, H, H, generator=g)
+    y = torch.randint(0, 10, (B,), generator=g)
+
+    model = ToyADM(3, seed=seed).eval()
+    cls = getattr(importlib.import_module(SU + "scheduling_dpm_2_uncertainty_centered"), "KDPM2SchedulerUncertaintyImagenetClassConditioned")
+    with contextlib.redirect_stdout(io.StringIO()):
+        rs = cls.from_config(base_config(**cfg), unet=model, **kw)
+        rs.set_timesteps(n_steps)
+        with seeded_noise(2000 + seed):
+            r = l4_sampling_loop(rs, model, x_T, y)
+
+    model = ToyADM(3, seed=seed).eval()
+    full = base_config(**cfg)        # (the oracle scheduler reads the default beta range; the cases keep it)
+    os_ = OracleDPM2Scheduler(None, **kw, **{k: full[k] for k in ("timestep_spacing", "steps_offset", "beta_schedule", "prediction_type",
+                                                                  "num_train_timesteps")}, variance_type=cfg.get("variance_type"))
+    os_.predict = lambda x, t: model(x, t, y=os_.prompt_embeds)[:, :3]
+    os_.set_timesteps(n_steps)
+    with seeded_noise(2000 + seed):
+        o = l4_sampling_loop(os_, model, x_T, y)
+    assert torch.equal(rs.timesteps, os_.timesteps) and r["uncertainty"].shape[1] > 0
+    for key in ("uncertainty", "score", "final"):
+        assert bits_equal(r[key], o[key]), key
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_oracle_sd_guidance_equals_live_reference(reference_on_path, seed):
+    """get_uncertainty_guided_score_with_percentile, posterior mode (uncertainty_guidance.py:61-131; the Stable Diffusion call site with
+    the CFG-doubled latent) for other latent sizes, M, percentiles and guidance scales than the fixture's"""
+    from tests.toy_models import ToySDUNet
+    import diffusion_uncertainty.uncertainty_guidance as ug
+    H, M, q, gs, t = [(16, 3, 0.8, 5.0, 801), (64, 16, 0.9, 7.5, 401), (8, 2, 0.5, 1.5, 21)][seed]
+    sd = ToySDUNet(4, seed=60 + seed).eval()
+    g = torch.Generator().manual_seed(600 + seed)
+    lat2 = torch.cat([torch.randn(1, 4, H, H, generator=g)] * 2)
+    emb = torch.randn(2, 8, 16, generator=g)
+    t_tensor = torch.tensor(t)
+    a_hat = torch.cumprod(1 - O.make_betas(), 0)[t]
+    saved = ug.use_posterior
+    ug.use_posterior = True
+    try:
+        with seeded_noise(5000 + seed), contextlib.redirect_stdout(io.StringIO()):
+            un, tx = sd(lat2, t_tensor, emb)[0].chunk(2)
+            eps = (un + gs * (tx - un)).detach().clone()
+            ref = ug.get_uncertainty_guided_score_with_percentile(eps, lat2.clone(), t_tensor, emb.clone(), sd, a_hat, q, "stable-diffusion",
+                                                                  num_uncertainty_samples=M, guidance_scale=gs).detach()
+    finally:
+        ug.use_posterior = saved
+    with torch.no_grad(), seeded_noise(5000 + seed):
+        un, tx = sd(lat2, t_tensor, emb)[0].chunk(2)
+        eps_o = un + gs * (tx - un)
+        x0 = (lat2 - torch.sqrt(1 - a_hat) * eps_o) / torch.sqrt(a_hat)
+        scores = []
+        for _ in range(M):
+            x_hat = O.perturb_add_noise(x0, torch.randn_like(eps_o), a_hat)
+            un, tx = sd(x_hat, t_tensor, emb)[0].chunk(2)
+            scores.append(un + gs * (tx - un))
+        u = O.variance_with_center(scores, eps_o)
+        out = O.posterior_blend(eps_o, u, O.calculate_threshold_map(q, None, u, "higher"), M, a_hat, batch_sum=True)
+    assert bits_equal(eps, eps_o) and bits_equal(ref, out)
