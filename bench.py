@@ -68,6 +68,21 @@ def l2_note(alg_bytes):
     return "L2-resident, latency-bound: %.1f MB per step per GPU, %d input copies rotate (%.0f MB in all, < L2)" % (mb, R, R * mb)
 
 
+def ulp_distance(a, b):
+    """largest distance, in units of the last place, between two fp32 tensors of one shape (inf if a NaN faces a number)"""
+    a, b = a.detach().cpu().float().flatten(), b.detach().cpu().float().flatten()
+    nan = torch.isnan(a)
+    if a.shape != b.shape or not torch.equal(nan, torch.isnan(b)):
+        return float("inf")
+    if bool(nan.all()):
+        return 0
+
+    def line(x):       # sign-magnitude bit patterns -> one monotone integer line (-0 and +0 coincide)
+        i = x[~nan].contiguous().view(torch.int32).long()
+        return torch.where(i < 0, -(i & 0x7FFFFFFF), i)
+    return int((line(a) - line(b)).abs().max())
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -389,10 +404,15 @@ class StepBench:
             raise AssertionError(f"parity: map differs from torch.var by {out['map_max_rel_diff_vs_reference_fp32']:.3e} relative")
         if self.fused:
             thr_k = self.plan.res["thr"]
-            thr_c = torch.quantile(u_k.flatten(1).cpu(), self.q, dim=1)    # (torch's CUDA lerp contracts to an FMA: compare on the host)
+            # torch.quantile of the kernel's own map, on the host.  The two order statistics are exact; the final lerp is rounded
+            # once per operation by the kernel (lerp_fma = 0), while torch contracts it into an FMA in its CUDA kernel and in the
+            # CPU kernels of FMA-capable builds: bit-identical where the host's torch does not contract (the B200 boxes so far), at
+            # most one unit in the last place otherwise — anything beyond that is a wrong order statistic and fails.
+            thr_c = torch.quantile(u_k.flatten(1).cpu(), self.q, dim=1)
             out["thr_bit_exact"] = bool(torch.equal(thr_k.cpu(), thr_c))
-            if not out["thr_bit_exact"]:
-                raise AssertionError("parity: thresholds are not bit-identical to torch.quantile of the map")
+            out["thr_max_ulp_vs_host_torch"] = ulp_distance(thr_k, thr_c)
+            if out["thr_max_ulp_vs_host_torch"] > 1:
+                raise AssertionError("parity: thresholds differ from torch.quantile of the map by more than the lerp's last bit")
             mask_k = (u_k > thr_k.view(-1, 1, 1, 1)).float()
         else:
             mask_k = (u_k > thr.view(-1, 1, 1, 1)).float()

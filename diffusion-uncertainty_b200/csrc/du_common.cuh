@@ -359,8 +359,8 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   return __uint_as_float(b);
 }
 
-// torch.lerp's two-branch formula (aten/native/Lerp.h).  fma = 0: one rounding per op (CPU kernel);
-// fma = 1: contracted like nvcc compiles torch's CUDA kernel.
+// torch.lerp's two-branch formula (aten/native/Lerp.h).  fma = 0: one rounding per op (torch's CPU kernel without FMA dispatch);
+// fma = 1: contracted like nvcc compiles torch's CUDA kernel (and like torch's vectorised CPU kernels on FMA hardware).
 __device__ __forceinline__ float lerp_torch(float a, float b, float w, int fma) {
   float diff = __fsub_rn(b, a);
   if (fabsf(w) < 0.5f) return fma ? __fmaf_rn(w, diff, a) : __fadd_rn(a, __fmul_rn(w, diff));

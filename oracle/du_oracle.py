@@ -80,16 +80,44 @@ def quantile_rank(n: int, q: float) -> Tuple[int, int, np.float32]:
     return lo, hi, np.float32(rank - np.float32(lo))
 
 
-def lerp_torch(a: np.float32, b: np.float32, w: np.float32) -> np.float32:
-    """torch.lerp's two-branch formula, one fp32 rounding per operation (no FMA), i.e. the CPU kernel."""
+def fma_f32(a, b, c) -> np.float32:
+    """a * b + c with ONE rounding to fp32 (round to nearest even) — what a hardware FMA returns —, computed exactly with rationals so
+    that the result does not depend on the host's own contraction."""
+    a, b, c = float(np.float32(a)), float(np.float32(b)), float(np.float32(c))
+    if not (math.isfinite(a) and math.isfinite(b) and math.isfinite(c)):
+        return np.float32(a * b + c)
+    from fractions import Fraction
+    exact = Fraction(a) * Fraction(b) + Fraction(c)
+    if exact == 0:
+        return np.float32(a * b + c)          # (signed zero as IEEE gives it)
+    mag = abs(exact)
+    e = mag.numerator.bit_length() - mag.denominator.bit_length()
+    if Fraction(2) ** e > mag:
+        e -= 1                                  # 2^e <= mag < 2^(e+1)
+    quantum = Fraction(2) ** (max(e, -126) - 23)
+    n, rem = divmod(mag, quantum)
+    n = int(n)
+    if rem * 2 > quantum or (rem * 2 == quantum and (n & 1)):
+        n += 1
+    val = float(n * quantum)                    # exact in double; 2^128 and above overflow to inf in the cast
+    with np.errstate(over="ignore"):
+        return np.float32(-val if exact < 0 else val)
+
+
+def lerp_torch(a: np.float32, b: np.float32, w: np.float32, fma: bool = False) -> np.float32:
+    """torch.lerp's two-branch formula (aten/native/Lerp.h).  fma=False: one fp32 rounding per operation.  fma=True: the multiply-add
+    of the selected branch fused — what torch's CUDA kernel does (nvcc contracts it) and what torch's CPU kernels do where they are
+    dispatched to an FMA-capable build (`vec::fmadd(coeff, end - start, base)`); which of the two a given host's torch.quantile
+    returns is a property of that host (tests/test_oracle_golden.py checks that it is one of them, row by row)."""
     a, b, w = np.float32(a), np.float32(b), np.float32(w)
     diff = np.float32(b - a)
     if abs(w) < np.float32(0.5):
-        return np.float32(a + np.float32(w * diff))
-    return np.float32(b - np.float32(diff * np.float32(np.float32(1.0) - w)))
+        return fma_f32(w, diff, a) if fma else np.float32(a + np.float32(w * diff))
+    omw = np.float32(np.float32(1.0) - w)
+    return fma_f32(-diff, omw, b) if fma else np.float32(b - np.float32(diff * omw))
 
 
-def quantile_linear_rows(u2d: Tensor, q: float) -> Tuple[Tensor, Tensor, Tensor]:
+def quantile_linear_rows(u2d: Tensor, q: float, lerp_fma: bool = False) -> Tuple[Tensor, Tensor, Tensor]:
     """Independent restatement of torch.quantile(u2d, q, dim=1) (sort -> two order statistics ->
     lerp).  Returns (threshold[B], rank_lo_hi[B,2] int64, values_lo_hi[B,2]).  A row that contains
     a NaN gives a NaN threshold (torch masks such rows explicitly).
@@ -108,7 +136,7 @@ def quantile_linear_rows(u2d: Tensor, q: float) -> Tuple[Tensor, Tensor, Tensor]
         # only the lo-th and hi-th order statistics are needed
         part = np.partition(row, (lo, hi))
         vals[b, 0], vals[b, 1] = part[lo], part[hi]
-        thr[b] = lerp_torch(part[lo], part[hi], w)
+        thr[b] = lerp_torch(part[lo], part[hi], w, lerp_fma)
     ranks = torch.tensor([[lo, hi]] * B, dtype=torch.int64)
     return torch.from_numpy(thr), ranks, torch.from_numpy(vals)
 

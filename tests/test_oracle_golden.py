@@ -26,6 +26,17 @@ def same(a, b):
     return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
 
 
+def restated_threshold_is(thr_torch, x2d, q):
+    """torch.quantile's threshold equals the restatement row by row, with the lerp rounded once per operation or fused — which one is
+    a property of the host's torch build / CPU (oracle.lerp_torch); everything in front of the lerp is exact"""
+    sep, _, _ = O.quantile_linear_rows(x2d, q, lerp_fma=False)
+    fus, _, _ = O.quantile_linear_rows(x2d, q, lerp_fma=True)
+    t = np.asarray(thr_torch, dtype=np.float32).reshape(-1)
+    ok = [(np.isnan(t[b]) and np.isnan(sep[b].item())) or t[b].view(np.int32) in (sep[b].numpy().view(np.int32), fus[b].numpy().view(np.int32))
+          for b in range(t.shape[0])]
+    return all(ok)
+
+
 SCHED_CASES = [
     # name, variant, ctor kwargs, n_steps, seed, eta, dropout, cfg
     ("sched_zigzag_centered", "zigzag_centered", dict(M=5, after_step=40, num_steps_uc=10, num_zigzag=3), 50, 0, 0.0, False, {}),
@@ -143,7 +154,7 @@ def test_quantile_restatement_is_torch_quantile(golden_dir):
     for tag in "abcdef":
         u, q = T(g[f"{tag}_u"]), float(g[f"{tag}_q"])
         thr, ranks, vals = O.quantile_linear_rows(u.flatten(1), q)
-        assert same(thr.numpy(), g[f"{tag}_thr"]), tag
+        assert restated_threshold_is(g[f"{tag}_thr"], u.flatten(1), q), tag       # (recorded from torch.quantile on the build host)
         kind = "higher" if bool(g[f"{tag}_higher"]) else "lower"
         assert same(O.calculate_threshold_map(q, None, u, kind).numpy(), g[f"{tag}_mask"]), tag
         # mask rebuilt from the restated threshold
@@ -162,14 +173,14 @@ def test_quantile_rank_known_answers(n, q, lo, w):
     assert l == lo and h == lo + 1 and abs(float(ww) - w) < 1e-4
     x = torch.rand(3, n, generator=torch.Generator().manual_seed(n)) ** 2
     thr, _, _ = O.quantile_linear_rows(x, q)
-    assert same(thr.numpy(), torch.quantile(x, q, dim=1).numpy())
+    assert restated_threshold_is(torch.quantile(x, q, dim=1).numpy(), x, q)
     assert int((x[0] > thr[0]).sum()) == n - 1 - lo  # tie-free row
 
 
 def test_quantile_edge_cases():
     x = torch.rand(2, 7)
     thr, _, _ = O.quantile_linear_rows(x, 0.5)
-    assert same(thr.numpy(), torch.quantile(x, 0.5, dim=1).numpy())
+    assert restated_threshold_is(torch.quantile(x, 0.5, dim=1).numpy(), x, 0.5)
     x[0, 3] = float("nan")
     thr, _, _ = O.quantile_linear_rows(x, 0.5)
     assert np.isnan(thr[0]) and not np.isnan(thr[1])
@@ -278,3 +289,43 @@ def test_oracle_second_order_pipeline_replays_the_reference(golden_dir):
         imgs, last = P.second_order_pipeline(model, T(g["x_T"]), T(g["y"]), float(g["q"]), batch_size=3, n_steps=8, start_step=2, num_steps=4,
                                              M=4, ac=ac)
     assert same(last.numpy(), g["final_last_batch"]) and same(imgs.numpy(), g["gen_images"])
+
+
+def test_quantile_restatement_equals_torch_quantile_property():
+    """hypothesis: the sort -> rank -> two-branch-lerp restatement (what the select kernels implement) reproduces torch.quantile(dim=1)
+    on the CPU for arbitrary row lengths, quantiles, value scales and ties: the two order statistics exactly, the threshold bit for bit
+    with the lerp either rounded per operation or fused (a property of the host: both forms are restated exactly)"""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(n=st.integers(1, 3000), B=st.integers(1, 3), q=st.floats(0.0, 1.0, width=32), seed=st.integers(0, 2 ** 31 - 1),
+           scale=st.sampled_from([1e-12, 1e-4, 1.0, 1e6]), levels=st.sampled_from([0, 3, 17, 256]))
+    def check(n, B, q, seed, scale, levels):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.rand(B, n, generator=g) * scale
+        if levels:
+            x = (torch.rand(B, n, generator=g) * levels).floor() * (scale / levels)      # ties (and exact zeros)
+        _, ranks, vals = O.quantile_linear_rows(x, q)
+        assert restated_threshold_is(torch.quantile(x, q, dim=1).numpy(), x, q), (n, q)
+        srt = torch.sort(x, dim=1).values
+        assert torch.equal(vals[:, 0], srt[:, int(ranks[0, 0])]) and torch.equal(vals[:, 1], srt[:, int(ranks[0, 1])])
+
+    check()
+
+
+def test_fused_multiply_add_restatement():
+    """oracle.fma_f32 (exact rational arithmetic, one rounding) against cases whose single-rounded value is known"""
+    f = np.float32
+    assert O.fma_f32(2, 3, -6) == 0 and O.fma_f32(3e38, 10, 0) == f(np.inf) and np.isnan(O.fma_f32(np.nan, 1, 1))
+    a = f(1.0 + 2.0 ** -12)                              # a^2 - 1 = 2^-11 + 2^-24: separate roundings lose the 2^-24, one rounding keeps it
+    assert O.fma_f32(a, a, -1.0) == f(2.0 ** -11 + 2.0 ** -24) and f(f(a * a) - f(1.0)) == f(2.0 ** -11)
+    assert f(2.0 ** -11 + 2.0 ** -24) != f(2.0 ** -11)
+    assert O.fma_f32(f(2.0 ** -100), f(2.0 ** -49), 0.0) == f(2.0 ** -149)      # smallest subnormal, exact
+    assert O.fma_f32(f(2.0 ** -100), f(2.0 ** -50), 0.0) == 0.0                 # half of it: ties to even
+    assert O.fma_f32(f(3 * 2.0 ** -100), f(2.0 ** -50), 0.0) == f(2.0 ** -148)  # 1.5 subnormal quanta: rounds to even (2)
+    rng = np.random.default_rng(3)
+    for _ in range(300):                                 # where the exact result fits a double, the double computation is the answer
+        x, y, z = f(rng.normal()), f(rng.normal()), f(rng.normal() * 1e-3)
+        d = float(x) * float(y) + float(z)
+        if float(f(d)) == d:
+            assert O.fma_f32(x, y, z) == f(d)
