@@ -99,9 +99,10 @@ int du_moments_merge(const float* const* means, const float* const* m2s, const i
  * PU/...posterior_distribution.py:15, uncertainty_guidance.py:112, generate_samples.py:946.
  * rank = fp32(q)*fp32(n-1); lo = floor, hi = ceil; thr = lerp(sorted[lo], sorted[hi], rank-lo) with
  * torch's two-branch lerp.  lerp_fma = 0 rounds the lerp once per operation (torch's CPU kernel where it
- * is not dispatched to an FMA build: the hosts of the B200 boxes), 1 fuses the multiply-add of the
- * selected branch (torch's CUDA kernel, and its CPU kernels on AVX2 / AVX-512 dispatch); the two differ
- * by at most one unit in the last place of the threshold.  A row containing NaN yields NaN.
+ * is not dispatched to an FMA build), 1 fuses the multiply-add of the selected branch (torch's CUDA
+ * kernel, and its CPU kernels on AVX2 / AVX-512 dispatch).  The two differ by at most one unit in the
+ * last place of the threshold, and only when the two order statistics are far apart relative to their
+ * value (short rows): for rows of thousands of elements they coincide.  A row containing NaN yields NaN.
  * thr_out[B]; rank_out[B][2] (nullable) = {lo, hi}; val_out[B][2] (nullable) = the two order
  * statistics.  scratch: du_quantile_scratch_bytes(B, n) bytes of device memory.
  * ---------------------------------------------------------------------------------------------- */

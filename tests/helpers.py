@@ -2,6 +2,35 @@
 import torch
 
 
+def host_quantile_without_contraction(real_quantile):
+    """A stand-in for torch.quantile in the GPU parity tests.  The checks there read "the kernel's threshold IS torch.quantile of the
+    kernel's own map, bit for bit", computed on the host.  torch.quantile's last step is a lerp whose multiply-add torch contracts into
+    an FMA on some hosts (AVX2 / AVX-512 dispatch of its CPU kernels) and not on others, one unit in the last place apart (oracle.lerp_torch);
+    the kernels' default is the uncontracted form.  For a 2-D fp32 CPU input reduced over dim 1 with a scalar q this returns the oracle's
+    exact restatement with the uncontracted lerp, after checking that the host's own torch.quantile is within that last bit of it; every
+    other call goes to torch unchanged (CUDA inputs in particular).  On a host that does not contract this is the identity."""
+    from oracle import du_oracle as O
+
+    def ulp_line(x):
+        i = x.contiguous().view(torch.int32).long()
+        return torch.where(i < 0, -(i & 0x7FFFFFFF), i)
+
+    def quantile(input, q, dim=None, keepdim=False, **kw):
+        ref = real_quantile(input, q, dim=dim, keepdim=keepdim, **kw)
+        if (kw or not isinstance(q, (int, float)) or not torch.is_tensor(input) or input.device.type != "cpu" or input.dtype != torch.float32
+                or input.dim() != 2 or dim not in (1, -1) or input.shape[0] == 0):
+            return ref
+        thr = O.quantile_linear_rows(input, float(q), lerp_fma=False)[0]
+        flat = ref.reshape(-1)
+        nan = torch.isnan(thr)
+        assert torch.equal(nan, torch.isnan(flat)), "NaN rows differ between torch.quantile and its restatement"
+        if not bool(nan.all()):
+            assert int((ulp_line(thr[~nan]) - ulp_line(flat[~nan])).abs().max()) <= 1, "torch.quantile is not within the lerp's last bit"
+        return thr.reshape(ref.shape)
+
+    return quantile
+
+
 def l4_sampling_loop(scheduler, model, x_T, y, eta=0.0, slice_channels=None):
     """The reference's L4 timestep loop around scheduler.step(), restated:
     diffusion_uncertainty/generate_samples.py:175-201 (class-conditioned, from tensor).

@@ -118,6 +118,36 @@ def test_bench_config_is_the_same_dictionary_in_both_arms():
     assert bench.input_ring(1.3e6) == bench.IN_RING_MAX and bench.l2_note(1.3e6).startswith("L2-resident")
 
 
+def test_host_quantile_stand_in_of_the_gpu_tests():
+    """tests/conftest.py routes torch.quantile of the GPU parity tests through this wrapper: uncontracted lerp whatever the host does"""
+    import numpy as np
+    import torch
+
+    from oracle import du_oracle as O
+    from tests.helpers import host_quantile_without_contraction
+    real = torch.quantile
+    hq = host_quantile_without_contraction(real)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(64, 3072, generator=g) ** 3
+    for q in (0.0, 0.333, 0.9, 0.95, 1.0):
+        want = O.quantile_linear_rows(x, q, lerp_fma=False)[0]
+        got = hq(x, q, dim=1)
+        assert got.shape == (64,) and np.array_equal(got.numpy().view(np.int32), want.numpy().view(np.int32))
+        assert hq(x, q, dim=1, keepdim=True).shape == (64, 1) and torch.equal(hq(x, q, dim=-1), got)
+        fused = O.quantile_linear_rows(x, q, lerp_fma=True)[0]
+        host = real(x, q, dim=1)
+        assert all(h in (a, b) for h, a, b in zip(host.numpy().view(np.int32), want.numpy().view(np.int32), fused.numpy().view(np.int32)))
+    x[3, 7] = float("nan")
+    got = hq(x, 0.5, dim=1)
+    assert torch.isnan(got[3]) and not torch.isnan(got[2])
+    # everything else is torch's own function, untouched
+    assert torch.equal(hq(x[0], 0.5), real(x[0], 0.5)) and torch.equal(hq(x.double()[:2], 0.5, dim=1), real(x.double()[:2], 0.5, dim=1))
+    assert torch.equal(hq(x[:2], torch.tensor([0.25, 0.5]), dim=1), real(x[:2], torch.tensor([0.25, 0.5]), dim=1))
+    assert torch.equal(hq(x[:2], 0.5, dim=0), real(x[:2], 0.5, dim=0))
+    with pytest.raises(RuntimeError):
+        hq(x, 1.5, dim=1)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "diffusion-uncertainty_b200")
     for dirpath, _, files in os.walk(pkg):
